@@ -1,0 +1,750 @@
+// gx_api.cu -- C ABI of libgxalign (include/gxalign.h): context, plans, kernel dispatch.
+// No CPU compute path exists in this file: every entry point needs a live sm_100 device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gxalign.h"
+#include "gx_fill.cuh"
+#include "gx_reads.cuh"
+#include "gx_walk.cuh"
+
+namespace gx {
+
+static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
+static_assert(sizeof(PairDesc) == 80, "PairDesc layout");
+static_assert(WARP_SMEM % 16 == 0, "per-warp smem must keep 16 B alignment");
+
+// ------------------------------------------------------------------------------------------------
+struct Block {
+    void *ptr;
+    size_t size;
+    bool free;
+};
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<Block> pool;
+    std::string last_error;
+    size_t pool_bytes = 0;
+};
+
+static Ctx *g_ctx = nullptr;
+static std::mutex g_mu;
+static thread_local std::string g_err;
+
+static int fail_cuda(cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_err = buf;
+    if (g_ctx) g_ctx->last_error = buf;
+    return GX_ERR_CUDA;
+}
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+// caching device allocator: plans are created per call by gx_align_pair/gx_align_batch
+static int pool_alloc(Ctx *c, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 511) & ~size_t(511);
+    int best = -1;
+    for (size_t k = 0; k < c->pool.size(); ++k) {
+        Block &b = c->pool[k];
+        if (b.free && b.size >= bytes && b.size <= 2 * bytes + (1u << 20))
+            if (best < 0 || b.size < c->pool[best].size) best = (int)k;
+    }
+    if (best >= 0) {
+        c->pool[best].free = false;
+        *out = c->pool[best].ptr;
+        return GX_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // release cached blocks and retry once
+        for (auto it = c->pool.begin(); it != c->pool.end();) {
+            if (it->free) {
+                cudaFree(it->ptr);
+                c->pool_bytes -= it->size;
+                it = c->pool.erase(it);
+            } else ++it;
+        }
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            g_err = "device allocation of " + std::to_string(bytes) + " bytes failed";
+            return GX_ERR_NOMEM;
+        }
+    }
+    c->pool.push_back({p, bytes, false});
+    c->pool_bytes += bytes;
+    *out = p;
+    return GX_OK;
+}
+static void pool_free(Ctx *c, void *p) {
+    if (!p) return;
+    for (auto &b : c->pool)
+        if (b.ptr == p) {
+            b.free = true;
+            return;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+enum PlanKind { KIND_WAVEFRONT = 0, KIND_READS = 1 };
+
+}  // namespace gx
+
+struct gx_plan {
+    gx::Ctx *ctx = nullptr;
+    int kind = gx::KIND_WAVEFRONT;
+    uint64_t n_pairs = 0;
+    gx_scores sc{};
+    int is_local = 0, flags = 0;
+    int K = 8;
+    int track = 0;
+    bool traceback = false;
+    std::vector<gx::PairDesc> pairs;   // host copy (offsets filled at upload)
+    std::vector<uint64_t> len1, len2;
+    uint64_t n_tiles = 0;
+    uint64_t cells = 0;
+    uint64_t code_bytes = 0, ops_bytes = 0, colbuf_entries = 0, top_entries = 0, progress_entries = 0, best_entries = 0;
+    uint64_t blob_cap = 0;
+    uint64_t max_len = 0;
+    // device
+    uint8_t *d_blob = nullptr;
+    gx::PairDesc *d_pairs = nullptr;
+    gx::TileDesc *d_tiles = nullptr;
+    uint32_t *d_ctrl = nullptr;  // [0] ticket, [16..] progress
+    unsigned long long *d_colbuf = nullptr;
+    int2 *d_top = nullptr;
+    uint8_t *d_codes = nullptr;
+    int4 *d_best = nullptr;
+    gx::DevResult *d_results = nullptr;
+    uint8_t *d_ops = nullptr;
+    // reads kind
+    uint64_t *d_off1 = nullptr, *d_off2 = nullptr;
+    uint32_t *d_len1 = nullptr, *d_len2 = nullptr;
+    int *d_scores = nullptr;
+    uint32_t parity = 0;
+    bool uploaded = false, executed = false, colbuf_dirty = true;
+    float fill_ms = 0, walk_ms = 0;
+    int launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0, dev_bytes = 0;
+    std::vector<uint8_t> ops_stage;
+};
+
+namespace gx {
+
+template <int K>
+static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
+    Ctx *c = pl->ctx;
+    const size_t smem = (size_t)WARPS_PER_CTA * WARP_SMEM;
+    void (*kern)(const FillParams) = nullptr;
+    const bool L = pl->is_local != 0, C = pl->traceback;
+    if (!L && !C) kern = gx_fill_kernel<K, false, false, 0>;
+    else if (!L && C) kern = gx_fill_kernel<K, false, true, 0>;
+    else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1>;
+    else if (L && !C) kern = gx_fill_kernel<K, true, false, 2>;
+    else kern = gx_fill_kernel<K, true, true, 2>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
+    if (occ < 1) occ = 1;
+    uint64_t want = (pl->n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    uint64_t cap = (uint64_t)c->sm_count * occ;
+    if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
+    int grid = (int)std::min<uint64_t>(want, cap);
+    if (grid < 1) grid = 1;
+    kern<<<grid, CTA_THREADS, smem, c->stream>>>(fp);
+    CK(cudaGetLastError());
+    return GX_OK;
+}
+
+template <int K>
+static int launch_walk(gx_plan *pl, const WalkParams &wp) {
+    gx_walk_kernel<K><<<(unsigned)pl->n_pairs, 32, 0, pl->ctx->stream>>>(wp);
+    CK(cudaGetLastError());
+    return GX_OK;
+}
+
+static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
+    if (!(sc.h <= 0 && sc.g < 0 && (long long)sc.h + sc.g < 0)) return GX_ERR_SCORES;
+    long long mx = std::max({std::llabs((long long)sc.s_match), std::llabs((long long)sc.s_mismatch), std::llabs((long long)sc.g)});
+    long long lim = 1ll << 29;
+    if (m > (1ull << 28) || n > (1ull << 28)) return GX_ERR_RANGE;
+    if ((long long)(m + n + 2) * mx + std::llabs((long long)sc.h) >= lim) return GX_ERR_RANGE;
+    if (local) {
+        long long vmax = (long long)std::min(m, n) * std::max<long long>(sc.s_match, 0);
+        if (vmax >= (1ll << 26)) return GX_ERR_RANGE;  // (V << log2 K) | k must stay in int32 for K <= 16
+    }
+    return GX_OK;
+}
+
+static void plan_release(gx_plan *pl) {
+    Ctx *c = pl->ctx;
+    void *ptrs[] = {pl->d_blob, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
+                    pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
+    for (void *p : ptrs) pool_free(c, p);
+}
+
+}  // namespace gx
+
+using namespace gx;
+
+// ================================================================================================
+extern "C" {
+
+const char *gx_version(void) { return "gxalign 0.1 (sm_100a)"; }
+
+const char *gx_strerror(int s) {
+    switch (s) {
+        case GX_OK: return "ok";
+        case GX_ERR_ARG: return "invalid argument";
+        case GX_ERR_SCORES: return "scores violate h <= 0, g < 0, h+g < 0";
+        case GX_ERR_RANGE: return "sequence lengths x scores exceed the int32 cell range";
+        case GX_ERR_OPS_CAP: return "ops buffer too small";
+        case GX_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU path)";
+        case GX_ERR_CUDA: return "CUDA error";
+        case GX_ERR_NOMEM: return "out of memory";
+        case GX_ERR_NOT_INIT: return "gx_init not called";
+        case GX_ERR_UNSUPPORTED: return "unsupported flag or mode";
+        case GX_ERR_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+
+const char *gx_last_error(void) { return g_err.c_str(); }
+
+int gx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int gx_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        g_err = "no CUDA device visible";
+        return GX_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return GX_ERR_NO_DEVICE;
+    }
+    if (device >= n) return GX_ERR_ARG;
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) {
+        g_err = "device is not compute capability 10.x; libgxalign carries sm_100a code only";
+        return GX_ERR_NO_DEVICE;
+    }
+    if (g_ctx && g_ctx->device == device) return GX_OK;
+    if (g_ctx) return GX_ERR_ARG;  // one context (one GPU) per process
+    CK(cudaSetDevice(device));
+    Ctx *c = new (std::nothrow) Ctx();
+    if (!c) return GX_ERR_NOMEM;
+    c->device = device;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CK(cudaEventCreate(&e));
+    g_ctx = c;
+    return GX_OK;
+}
+
+void gx_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return;
+    cudaSetDevice(g_ctx->device);
+    cudaStreamSynchronize(g_ctx->stream);
+    for (auto &b : g_ctx->pool) cudaFree(b.ptr);
+    for (auto &e : g_ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx;
+    g_ctx = nullptr;
+}
+
+int gx_check_scores(gx_scores sc, uint64_t m, uint64_t n) { return check_scores_impl(sc, m, n, true); }
+
+int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t start_j, uint32_t *ops_i, uint32_t *ops_j) {
+    if ((!ops && n_ops) || !ops_i || !ops_j) return GX_ERR_ARG;
+    uint64_t i = start_i, j = start_j;
+    for (uint64_t k = 0; k < n_ops; ++k) {
+        ops_i[k] = (uint32_t)i;
+        ops_j[k] = (uint32_t)j;
+        switch (ops[k]) {
+            case GX_MATCH:
+            case GX_MISMATCH:
+                i = i ? i - 1 : 0;
+                j = j ? j - 1 : 0;
+                break;
+            case GX_INSERT:
+            case GX_OPEN_INSERT: j = j ? j - 1 : 0; break;
+            case GX_DELETE:
+            case GX_OPEN_DELETE: i = i ? i - 1 : 0; break;
+            default: return GX_ERR_ARG;
+        }
+    }
+    return GX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
+                   gx_plan **out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out) return GX_ERR_ARG;
+    *out = nullptr;
+    if (!g_ctx) return GX_ERR_NOT_INIT;
+    if ((!len1 || !len2) && n_pairs) return GX_ERR_ARG;
+    if (flags & GX_FLAG_LCS_AT_MAX) return GX_ERR_UNSUPPORTED;
+    if (n_pairs >= (1ull << 31)) return GX_ERR_RANGE;
+    Ctx *c = g_ctx;
+    CK(cudaSetDevice(c->device));
+    uint64_t max_len = 0;
+    for (uint64_t q = 0; q < n_pairs; ++q) {
+        int rc = check_scores_impl(sc, len1[q], len2[q], is_local != 0);
+        if (rc) return rc;
+        max_len = std::max({max_len, len1[q], len2[q]});
+    }
+    if (n_pairs == 0) {
+        int rc = check_scores_impl(sc, 0, 0, is_local != 0);
+        if (rc) return rc;
+    }
+    gx_plan *pl = new (std::nothrow) gx_plan();
+    if (!pl) return GX_ERR_NOMEM;
+    pl->ctx = c;
+    pl->n_pairs = n_pairs;
+    pl->sc = sc;
+    pl->is_local = is_local ? 1 : 0;
+    pl->flags = flags;
+    pl->traceback = (flags & GX_FLAG_TRACEBACK) != 0;
+    pl->track = is_local ? ((pl->traceback || (flags & GX_FLAG_START_CELL)) ? 2 : 1) : 0;
+    pl->len1.assign(len1, len1 + n_pairs);
+    pl->len2.assign(len2, len2 + n_pairs);
+    pl->max_len = max_len;
+    for (uint64_t q = 0; q < n_pairs; ++q) pl->cells += (len1[q] + 1) * (len2[q] + 1);
+
+    // short-read batches without traceback go to the inter-task kernel (K4)
+    const bool reads = !pl->traceback && pl->track != 2 && n_pairs >= 1024 && max_len <= (uint64_t)READS_MAX_LEN &&
+                       (!is_local || sc.s_mismatch < 0);
+    pl->kind = reads ? KIND_READS : KIND_WAVEFRONT;
+    int rc = GX_OK;
+    auto A = [&](size_t bytes, void **p) {
+        if (rc == GX_OK) {
+            rc = pool_alloc(c, bytes, p);
+            if (rc == GX_OK) pl->dev_bytes += (bytes + 511) & ~size_t(511);
+        }
+    };
+    if (pl->kind == KIND_READS) {
+        A(n_pairs * 8, (void **)&pl->d_off1);
+        A(n_pairs * 8, (void **)&pl->d_off2);
+        A(n_pairs * 4, (void **)&pl->d_len1);
+        A(n_pairs * 4, (void **)&pl->d_len2);
+        A(n_pairs * 4, (void **)&pl->d_scores);
+        if (rc == GX_OK) {
+            std::vector<uint32_t> l1(n_pairs), l2(n_pairs);
+            for (uint64_t q = 0; q < n_pairs; ++q) {
+                l1[q] = (uint32_t)len1[q];
+                l2[q] = (uint32_t)len2[q];
+            }
+            cudaError_t e = cudaMemcpyAsync(pl->d_len1, l1.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_len2, l2.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail_cuda(e, "upload lengths");
+        }
+        if (rc != GX_OK) {
+            plan_release(pl);
+            delete pl;
+            return rc;
+        }
+        *out = pl;
+        return GX_OK;
+    }
+
+    // ---- wavefront geometry
+    pl->K = 8;
+    const int K = pl->K, W = 32 * K;
+    const int GROUPS = 32 / (64 / K);
+    pl->pairs.resize(n_pairs);
+    std::vector<TileDesc> tiles;
+    std::vector<uint64_t> keys;
+    uint64_t colbuf = 0, top = 0, codes = 0, ops = 0, progress = 0, best = 0;
+    for (uint64_t q = 0; q < n_pairs; ++q) {
+        PairDesc &pd = pl->pairs[q];
+        memset(&pd, 0, sizeof pd);
+        const uint64_t m = len1[q], n = len2[q];
+        pd.m = (uint32_t)m;
+        pd.n = (uint32_t)n;
+        const bool interior = m > 0 && n > 0;
+        pd.S = interior ? (uint32_t)((n + W - 1) / W) : 0;
+        pd.P = interior ? (uint32_t)((m + PANEL_H - 1) / PANEL_H) : 0;
+        pd.colbuf_off = colbuf;
+        pd.top_off = top;
+        pd.codes_off = codes;
+        pd.ops_off = ops;
+        pd.progress_off = (uint32_t)progress;
+        pd.tile_base = (uint32_t)best;
+        const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
+        pd.tile_code_bytes = interior ? tile_blocks(rows_max) * GROUPS * 32 * 16 : 0;
+        if (interior) {
+            colbuf += (uint64_t)(pd.S - 1) * m;
+            top += n;
+            progress += pd.S;
+            if (progress >= (1ull << 32) || best + (uint64_t)pd.S * pd.P >= (1ull << 32)) {
+                delete pl;
+                return GX_ERR_RANGE;
+            }
+            best += (uint64_t)pd.S * pd.P;
+            if (pl->traceback) codes += (uint64_t)pd.S * pd.P * pd.tile_code_bytes;
+        }
+        if (pl->traceback) ops += ((m + n + 1) + 31) & ~uint64_t(31);
+        // ticket order: every dependency of (p,s) -- (p,s-1) and (p-1,s) -- gets a smaller key.
+        for (uint32_t p = 0; p < pd.P; ++p)
+            for (uint32_t s = 0; s < pd.S; ++s) {
+                tiles.push_back({(uint32_t)q, p, s, 0});
+                keys.push_back(((uint64_t)p * PANEL_H + (uint64_t)s * 96) << 24 | (q & 0xffffff));
+            }
+    }
+    {
+        std::vector<uint32_t> idx(tiles.size());
+        for (size_t k = 0; k < idx.size(); ++k) idx[k] = (uint32_t)k;
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+        std::vector<TileDesc> sorted(tiles.size());
+        for (size_t k = 0; k < idx.size(); ++k) sorted[k] = tiles[idx[k]];
+        tiles.swap(sorted);
+    }
+    pl->n_tiles = tiles.size();
+    if (pl->n_tiles >= (1ull << 32) - 65536) {
+        delete pl;
+        return GX_ERR_RANGE;
+    }
+    pl->code_bytes = codes;
+    pl->ops_bytes = ops;
+    pl->colbuf_entries = colbuf;
+    pl->top_entries = top;
+    pl->progress_entries = progress;
+    pl->best_entries = best;
+
+    A(n_pairs * sizeof(PairDesc), (void **)&pl->d_pairs);
+    A(tiles.size() * sizeof(TileDesc), (void **)&pl->d_tiles);
+    A((16 + progress) * 4, (void **)&pl->d_ctrl);
+    A(colbuf * 8, (void **)&pl->d_colbuf);
+    A(top * 8, (void **)&pl->d_top);
+    if (pl->traceback) A(codes, (void **)&pl->d_codes);
+    if (pl->is_local) A(best * 16, (void **)&pl->d_best);
+    A(n_pairs * sizeof(DevResult), (void **)&pl->d_results);
+    if (pl->traceback) A(ops, (void **)&pl->d_ops);
+    if (rc == GX_OK && !tiles.empty()) {
+        cudaError_t e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "upload tiles");
+    }
+    if (rc != GX_OK) {
+        plan_release(pl);
+        delete pl;
+        return rc;
+    }
+    *out = pl;
+    return GX_OK;
+}
+
+int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *off2) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pl || (!blob && blob_len) || ((!off1 || !off2) && pl->n_pairs)) return GX_ERR_ARG;
+    Ctx *c = pl->ctx;
+    CK(cudaSetDevice(c->device));
+    for (uint64_t q = 0; q < pl->n_pairs; ++q)
+        if (off1[q] + pl->len1[q] > blob_len || off2[q] + pl->len2[q] > blob_len) return GX_ERR_ARG;
+    if (!pl->d_blob || pl->blob_cap < blob_len + 64) {
+        pool_free(c, pl->d_blob);
+        pl->d_blob = nullptr;
+        int rc = pool_alloc(c, blob_len + 64, (void **)&pl->d_blob);
+        if (rc) return rc;
+        pl->blob_cap = blob_len + 64;
+        pl->dev_bytes += blob_len + 64;
+    }
+    if (blob_len) CK(cudaMemcpyAsync(pl->d_blob, blob, blob_len, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(pl->d_blob + blob_len, 0, 64, c->stream));
+    pl->h2d_bytes = blob_len;
+    if (pl->kind == KIND_READS) {
+        if (pl->n_pairs) {
+            CK(cudaMemcpyAsync(pl->d_off1, off1, pl->n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(pl->d_off2, off2, pl->n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+            pl->h2d_bytes += pl->n_pairs * 16;
+        }
+    } else {
+        for (uint64_t q = 0; q < pl->n_pairs; ++q) {
+            pl->pairs[q].s1_off = off1[q];
+            pl->pairs[q].s2_off = off2[q];
+        }
+        if (pl->n_pairs) {
+            CK(cudaMemcpyAsync(pl->d_pairs, pl->pairs.data(), pl->n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
+            pl->h2d_bytes += pl->n_pairs * sizeof(PairDesc);
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    pl->uploaded = true;
+    return GX_OK;
+}
+
+int gx_plan_execute(gx_plan *pl) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pl) return GX_ERR_ARG;
+    if (!pl->uploaded) return GX_ERR_ARG;
+    Ctx *c = pl->ctx;
+    CK(cudaSetDevice(c->device));
+    pl->launches = 0;
+    pl->fill_ms = pl->walk_ms = 0;
+    const gx_scores sc = pl->sc;
+    if (pl->n_pairs == 0) {
+        pl->executed = true;
+        return GX_OK;
+    }
+    if (pl->kind == KIND_READS) {
+        ReadsParams rp;
+        rp.blob = pl->d_blob;
+        rp.off1 = pl->d_off1;
+        rp.off2 = pl->d_off2;
+        rp.len1 = pl->d_len1;
+        rp.len2 = pl->d_len2;
+        rp.n_pairs = (uint32_t)pl->n_pairs;
+        rp.scores = pl->d_scores;
+        rp.results = nullptr;
+        rp.a = sc.s_match;
+        rp.b = sc.s_mismatch;
+        rp.g = sc.g;
+        rp.h = sc.h;
+        rp.is_local = pl->is_local;
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        int rc = launch_reads(rp, (int)pl->max_len, c->sm_count, c->stream);
+        if (rc == -1) return GX_ERR_UNSUPPORTED;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventElapsedTime(&pl->fill_ms, c->ev[0], c->ev[1]));
+        pl->launches = 1;
+        pl->executed = true;
+        return GX_OK;
+    }
+
+    CK(cudaEventRecord(c->ev[0], c->stream));   // the step's device time includes its own control-word reset
+    if (pl->colbuf_dirty && pl->colbuf_entries) {
+        CK(cudaMemsetAsync(pl->d_colbuf, 0xff, pl->colbuf_entries * 8, c->stream));  // parity bit 1 everywhere
+        pl->parity = 0;
+    }
+    pl->colbuf_dirty = true;  // until this execute completes
+    CK(cudaMemsetAsync(pl->d_ctrl, 0, (16 + pl->progress_entries) * 4, c->stream));
+    FillParams fp;
+    fp.blob = pl->d_blob;
+    fp.pairs = pl->d_pairs;
+    fp.tiles = pl->d_tiles;
+    fp.n_tiles = (uint32_t)pl->n_tiles;
+    fp.parity = pl->parity;
+    fp.ticket = pl->d_ctrl;
+    fp.progress = pl->d_ctrl + 16;
+    fp.colbuf = pl->d_colbuf;
+    fp.top = pl->d_top;
+    fp.codes = pl->d_codes;
+    fp.tile_best = pl->d_best;
+    fp.g = sc.g;
+    fp.h = sc.h;
+    fp.hg = sc.h + sc.g;
+    fp.ap = sc.s_match - fp.hg;
+    fp.bp = sc.s_mismatch - fp.hg;
+    if (pl->n_tiles) {
+        int rc = launch_fill<8>(pl, fp, 0);
+        if (rc) return rc;
+        pl->launches++;
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    WalkParams wp;
+    wp.blob = pl->d_blob;
+    wp.pairs = pl->d_pairs;
+    wp.n_pairs = (uint32_t)pl->n_pairs;
+    wp.top = pl->d_top;
+    wp.codes = pl->d_codes;
+    wp.tile_best = pl->d_best;
+    wp.results = pl->d_results;
+    wp.ops = pl->d_ops;
+    wp.g = sc.g;
+    wp.h = sc.h;
+    wp.hg = fp.hg;
+    wp.kcols_log2 = 3;
+    wp.is_local = pl->is_local;
+    wp.traceback = pl->traceback ? 1 : 0;
+    wp.have_best = pl->track == 2 ? 1 : 0;
+    {
+        int rc = launch_walk<8>(pl, wp);
+        if (rc) return rc;
+        pl->launches++;
+    }
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    uint32_t abort_word = 0;
+    CK(cudaMemcpyAsync(&abort_word, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (abort_word) {
+        g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";
+        return GX_ERR_INTERNAL;
+    }
+    CK(cudaEventElapsedTime(&pl->fill_ms, c->ev[0], c->ev[1]));
+    CK(cudaEventElapsedTime(&pl->walk_ms, c->ev[1], c->ev[2]));
+    pl->parity ^= 1u;
+    pl->colbuf_dirty = false;
+    pl->executed = true;
+    return GX_OK;
+}
+
+int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pl || (!out && pl->n_pairs)) return GX_ERR_ARG;
+    if (!pl->executed) return GX_ERR_ARG;
+    if (pl->traceback && pl->n_pairs && (!ops_blob || !ops_off)) return GX_ERR_ARG;
+    Ctx *c = pl->ctx;
+    CK(cudaSetDevice(c->device));
+    if (pl->n_pairs == 0) return GX_OK;
+    if (pl->kind == KIND_READS) {
+        std::vector<int> sc32(pl->n_pairs);
+        CK(cudaMemcpyAsync(sc32.data(), pl->d_scores, pl->n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        pl->d2h_bytes = pl->n_pairs * 4;
+        for (uint64_t q = 0; q < pl->n_pairs; ++q) {
+            gx_result r;
+            memset(&r, 0, sizeof r);
+            r.score = sc32[q];
+            r.start_i = r.end_i = pl->len1[q];
+            r.start_j = r.end_j = pl->len2[q];
+            r.fill_ms = pl->fill_ms;
+            out[q] = r;
+        }
+        return GX_OK;
+    }
+    CK(cudaMemcpyAsync(out, pl->d_results, pl->n_pairs * sizeof(gx_result), cudaMemcpyDeviceToHost, c->stream));
+    pl->d2h_bytes = pl->n_pairs * sizeof(gx_result);
+    if (pl->traceback) {
+        pl->ops_stage.resize(pl->ops_bytes);
+        CK(cudaMemcpyAsync(pl->ops_stage.data(), pl->d_ops, pl->ops_bytes, cudaMemcpyDeviceToHost, c->stream));
+        pl->d2h_bytes += pl->ops_bytes;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    int rc = GX_OK;
+    for (uint64_t q = 0; q < pl->n_pairs; ++q) {
+        out[q].fill_ms = pl->fill_ms;
+        out[q].walk_ms = pl->walk_ms;
+        if (pl->traceback) {
+            const uint64_t cap = ops_off[q + 1] - ops_off[q];
+            if (out[q].n_ops > cap) {
+                rc = GX_ERR_OPS_CAP;
+                continue;
+            }
+            memcpy(ops_blob + ops_off[q], pl->ops_stage.data() + pl->pairs[q].ops_off, out[q].n_ops);
+        }
+    }
+    return rc;
+}
+
+int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pl || (!scores && pl->n_pairs)) return GX_ERR_ARG;
+    if (!pl->executed) return GX_ERR_ARG;
+    Ctx *c = pl->ctx;
+    CK(cudaSetDevice(c->device));
+    if (pl->n_pairs == 0) return GX_OK;
+    if (pl->kind == KIND_READS) {
+        // int32 on the wire (4 B per pair), widened on the host
+        std::vector<int> sc32(pl->n_pairs);
+        CK(cudaMemcpyAsync(sc32.data(), pl->d_scores, pl->n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        pl->d2h_bytes = pl->n_pairs * 4;
+        for (uint64_t q = 0; q < pl->n_pairs; ++q) scores[q] = sc32[q];
+        return GX_OK;
+    }
+    std::vector<gx_result> res(pl->n_pairs);
+    CK(cudaMemcpyAsync(res.data(), pl->d_results, pl->n_pairs * sizeof(gx_result), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    pl->d2h_bytes = pl->n_pairs * sizeof(gx_result);
+    for (uint64_t q = 0; q < pl->n_pairs; ++q) scores[q] = res[q].score;
+    return GX_OK;
+}
+
+double gx_plan_stat(const gx_plan *pl, int what) {
+    if (!pl) return -1.0;
+    switch (what) {
+        case 0: return pl->fill_ms;
+        case 1: return pl->walk_ms;
+        case 2: return pl->launches;
+        case 3: return (double)pl->cells;
+        case 4: return (double)pl->code_bytes;
+        case 5: return (double)pl->dev_bytes;
+        case 6: return (double)pl->h2d_bytes;
+        case 7: return (double)pl->d2h_bytes;
+        case 8: return (double)pl->n_tiles;
+        case 9: return (double)pl->kind;
+        default: return -1.0;
+    }
+}
+
+void gx_plan_destroy(gx_plan *pl) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pl) return;
+    plan_release(pl);
+    delete pl;
+}
+
+int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,
+                   const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags, gx_result *out,
+                   uint8_t *ops_blob, const uint64_t *ops_off) {
+    gx_plan *pl = nullptr;
+    int rc = gx_plan_create(len1, len2, n_pairs, sc, is_local, flags, &pl);
+    if (rc) return rc;
+    rc = gx_plan_upload(pl, seq_blob, blob_len, off1, off2);
+    if (!rc) rc = gx_plan_execute(pl);
+    if (!rc) rc = gx_plan_fetch(pl, out, ops_blob, ops_off);
+    gx_plan_destroy(pl);
+    return rc;
+}
+
+int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,
+                   const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int64_t *scores) {
+    gx_plan *pl = nullptr;
+    int rc = gx_plan_create(len1, len2, n_pairs, sc, is_local, 0, &pl);
+    if (rc) return rc;
+    rc = gx_plan_upload(pl, seq_blob, blob_len, off1, off2);
+    if (!rc) rc = gx_plan_execute(pl);
+    if (!rc) rc = gx_plan_fetch_scores(pl, scores);
+    gx_plan_destroy(pl);
+    return rc;
+}
+
+int gx_align_pair(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local, int flags,
+                  gx_result *out, uint8_t *ops, uint64_t ops_cap) {
+    if (!out || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
+    if ((flags & GX_FLAG_TRACEBACK) && (!ops || ops_cap < m + n + 1)) return (!ops) ? GX_ERR_ARG : GX_ERR_OPS_CAP;
+    std::vector<uint8_t> blob(m + n);
+    if (m) memcpy(blob.data(), s1, m);
+    if (n) memcpy(blob.data() + m, s2, n);
+    uint64_t off1 = 0, off2 = m, l1 = m, l2 = n;
+    uint64_t ops_off[2] = {0, ops_cap};
+    return gx_align_batch(blob.data(), m + n, &off1, &l1, &off2, &l2, 1, sc, is_local, flags, out, ops, ops_off);
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// gx_common.cuh -- shared device/host definitions of libgxalign (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gx {
+
+// "minus infinity" of the int32 cell state; the reference uses i64::MIN + |g+h| (algo.rs:166)
+constexpr int NEG32 = -(1 << 30);
+
+// Rows of one panel: a tile is (panel p, strip s) = PANEL_H rows x 32*K columns, owned by one warp.
+constexpr int PANEL_H_LOG2 = 12;
+constexpr int PANEL_H = 1 << PANEL_H_LOG2;
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+
+// per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
+// the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.
+constexpr int WARP_SMEM_S1 = PANEL_H + 32;
+constexpr int WARP_SMEM = WARP_SMEM_S1 + 256 + 256 + 16;
+
+struct PairDesc {
+    uint64_t s1_off, s2_off;   // byte offsets of the two sequences in the device blob
+    uint64_t colbuf_off;       // u64 entries: strip s (< S-1) right boundary column, row i (1..m) at colbuf_off + s*m + (i-1)
+    uint64_t top_off;          // int2 entries: column j (1..n) at top_off + (j-1): (E,D) of the last finished panel row
+    uint64_t codes_off;        // bytes: tile (p,s) at codes_off + (p*S+s)*tile_code_bytes
+    uint64_t ops_off;          // bytes in the device ops blob
+    uint32_t m, n;
+    uint32_t S, P;             // strips, panels
+    uint32_t progress_off;     // u32 entries: progress[s] = panels finished by strip s
+    uint32_t tile_base;        // tile_best index of tile (0,0); tile (p,s) at tile_base + p*S + s
+    uint32_t tile_code_bytes;
+    uint32_t pad_;
+};
+
+struct TileDesc {
+    uint32_t pair, p, s, pad_;
+};
+
+// device copy of gx_result (include/gxalign.h) -- identical layout, checked by static_assert in gx_api.cu
+struct DevResult {
+    long long score;
+    unsigned long long start_i, start_j, end_i, end_j, n_ops, matches, mismatches, gap_extensions, opening_gaps, lcs_at_first_max;
+    double fill_ms, walk_ms;
+};
+
+struct FillParams {
+    const uint8_t *blob;
+    const PairDesc *pairs;
+    const TileDesc *tiles;
+    uint32_t n_tiles;
+    uint32_t parity;                 // LL parity bit of this execute (SURVEY "boundary hand-off")
+    uint32_t *ticket;
+    uint32_t *progress;
+    unsigned long long *colbuf;
+    int2 *top;
+    uint8_t *codes;
+    int4 *tile_best;
+    int g, hg, ap, bp, h;            // ap = s_match - (h+g), bp = s_mismatch - (h+g): S is formed in E-space (E = V + h + g)
+};
+
+struct WalkParams {
+    const uint8_t *blob;
+    const PairDesc *pairs;
+    uint32_t n_pairs;
+    const int2 *top;
+    const uint8_t *codes;
+    const int4 *tile_best;
+    DevResult *results;
+    uint8_t *ops;
+    int g, hg, h;
+    int kcols_log2;                  // log2(K) of the fill kernel that wrote the codes
+    int is_local, traceback, have_best;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int2 ld_cg_int2(const int2 *p) {
+    int2 v;
+    asm volatile("ld.global.cg.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg_int2(int2 *p, int2 v) {
+    asm volatile("st.global.cg.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cs_uint4(uint4 *p, uint4 v) {
+    // streaming store: traceback codes are written once and read only along the path
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int N>
+struct Log2 {
+    static constexpr int value = 1 + Log2<N / 2>::value;
+};
+template <>
+struct Log2<1> {
+    static constexpr int value = 0;
+};
+
+}  // namespace gx

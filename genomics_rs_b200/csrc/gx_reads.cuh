@@ -1,0 +1,150 @@
+// gx_reads.cuh -- K4: inter-task batch kernel for many short pairs (score only).
+//
+// Same recurrences as gx_fill.cuh (reference: /root/reference/src/alignment/algo.rs:191-268), but the
+// unit of parallelism is the PAIR: a group of G lanes owns one pair, each lane K register-blocked
+// columns (G*K >= n), rows flow through the group as a systolic skew with two shuffles per step.
+// No shared memory, no inter-warp traffic, no traceback storage.
+//
+// Local mode needs no masking at all: rows above/below the table and columns right of it are fed a
+// never-matching character, which (for s_mismatch < 0) makes every such cell strictly smaller than a
+// real cell it derives from, so the running maximum is unaffected.  Global mode freezes a lane's
+// state outside rows 0..m-1 (two selects per cell) and reads E[m][n] from the lane that owns column n.
+#pragma once
+#include "gx_common.cuh"
+
+namespace gx {
+
+constexpr int READS_MAX_LEN = 640;
+
+struct ReadsParams {
+    const uint8_t *blob;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    uint32_t n_pairs;
+    int *scores;
+    DevResult *results;   // may be null
+    int a, b, g, h, is_local;
+};
+
+template <int G, int K, bool LOCAL>
+__global__ void __launch_bounds__(256) gx_reads_kernel(const ReadsParams P) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int GPW = 32 / G;  // groups per warp
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % G;     // lane in group
+    const int gw = lane / G;     // group in warp
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int g = P.g, hg = P.h + P.g, h = P.h;
+    const int ap = P.a - hg, bp = P.b - hg;
+
+    for (uint64_t base = (uint64_t)warp_global * GPW; base < P.n_pairs; base += (uint64_t)n_warps * GPW) {
+        const uint64_t q = base + gw;
+        const bool have = q < P.n_pairs;
+        const int m = have ? (int)P.len1[q] : 0;
+        const int n = have ? (int)P.len2[q] : 0;
+        const uint8_t *s1 = P.blob + (have ? P.off1[q] : 0);
+        const uint8_t *s2 = P.blob + (have ? P.off2[q] : 0);
+        const int jl = lg * K;
+        int c2[K], eu[K], du[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c2[k] = (jl + k < n) ? (int)__ldg(s2 + jl + k) : 256;
+            eu[k] = (LOCAL ? 0 : h + (jl + k + 1) * g) + hg;
+            du[k] = NEG32;
+        }
+        int vd = ((jl == 0) ? 0 : (LOCAL ? 0 : h + jl * g)) + hg;  // E of (row 0, column jl)
+        // every lane of the group must finish row m-1; the warp runs the longest group's step count
+        const int lstar = (n > 0) ? (n - 1) / K : 0;
+        int steps = (m > 0 && n > 0) ? m + G - 1 : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) steps = max(steps, __shfl_xor_sync(FULLM, steps, off));
+
+        // local: lanes that have not reached row 0 yet must see "V = 0, I = 0" from their left neighbour
+        int elast = LOCAL ? hg : 0, ilast = 0, best = 0;
+        int c1n = (m > 0 && lg == 0) ? (int)__ldg(s1) : -1;
+        for (int t = 0; t < steps; ++t) {
+            const int r = t - lg;
+            const int c1 = c1n;
+            {   // prefetch next row's character (address independent of the DP state)
+                const int rn = r + 1;
+                c1n = (rn >= 0 && rn < m) ? (int)__ldg(s1 + rn) : -1;
+            }
+            int el = __shfl_up_sync(FULLM, elast, 1);
+            int il = __shfl_up_sync(FULLM, ilast, 1);
+            if (lg == 0) {
+                el = (LOCAL ? 0 : h + (r + 1) * g) + hg;  // column 0: V = delete_score (algo.rs:204-211)
+                il = NEG32;
+            }
+            const bool active = LOCAL ? true : (r >= 0 && r < m);  // global: state is frozen outside rows 0..m-1
+            int e = el, irun = il, ed = vd;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int In = LOCAL ? __viaddmax_s32_relu(irun, g, e) : __viaddmax_s32(irun, g, e);
+                const int Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
+                const int Sn = ed + ((c1 == c2[k]) ? ap : bp);
+                const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
+                ed = eu[k];
+                const int En = Vn + hg;
+                if (LOCAL) {
+                    eu[k] = En;
+                    du[k] = Dn;
+                    best = max(best, Vn);
+                } else {
+                    eu[k] = active ? En : eu[k];
+                    du[k] = active ? Dn : du[k];
+                }
+                e = En;
+                irun = In;
+            }
+            vd = active ? el : vd;
+            elast = e;
+            ilast = irun;
+        }
+        int score;
+        if (LOCAL) {
+            score = best;
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) score = max(score, __shfl_xor_sync(FULLM, score, off));
+            if (m == 0 || n == 0) score = 0;
+        } else {
+            // the owner of column n holds E[m][n] in eu[(n-1)%K] (frozen after row m-1)
+            int v = 0;
+            const int kk = (n > 0) ? (n - 1) % K : 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (k == kk) v = eu[k];
+            v = __shfl_sync(FULLM, v, gw * G + lstar);
+            score = v - hg;
+            if (m == 0 && n == 0) score = 0;
+            else if (m == 0) score = h + n * g;
+            else if (n == 0) score = h + m * g;
+        }
+        if (have && lg == 0) {
+            P.scores[q] = score;
+        }
+    }
+}
+
+template <int G, int K>
+static int launch_reads_gk(const ReadsParams &rp, int sm_count, cudaStream_t st) {
+    const int threads = 256;
+    const uint64_t groups_per_cta = (uint64_t)(threads / 32) * (32 / G);
+    uint64_t want = (rp.n_pairs + groups_per_cta - 1) / groups_per_cta;
+    uint64_t cap = (uint64_t)sm_count * 8;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    if (rp.is_local) gx_reads_kernel<G, K, true><<<grid, threads, 0, st>>>(rp);
+    else gx_reads_kernel<G, K, false><<<grid, threads, 0, st>>>(rp);
+    return 0;
+}
+
+// returns -1 if max_len is not supported by this kernel family
+static int launch_reads(const ReadsParams &rp, int max_len, int sm_count, cudaStream_t st) {
+    if (max_len <= 8 * 19) return launch_reads_gk<8, 19>(rp, sm_count, st);
+    if (max_len <= 16 * 20) return launch_reads_gk<16, 20>(rp, sm_count, st);
+    if (max_len <= 32 * 20) return launch_reads_gk<32, 20>(rp, sm_count, st);
+    return -1;
+}
+
+}  // namespace gx

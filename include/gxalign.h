@@ -1,0 +1,144 @@
+/*
+ * gxalign.h -- C ABI of libgxalign: B200-native (sm_100a) affine-gap global (NW) / local (SW)
+ * alignment, the drop-in for the one hot path of nlaha/genomics-rs:
+ *
+ *     alignment_table(&SequenceContainer,&Scores,is_local,reverse) -> (Array2<AlignmentCell>, usize)
+ *                                                        /root/reference/src/alignment/algo.rs:151-156
+ *     retrace(&SequenceContainer, Array2<AlignmentCell>, is_local) -> AlignedSequences
+ *                                                        /root/reference/src/alignment/algo.rs:287-291
+ *
+ * The reference joins the two with an owned 48-byte-per-cell table (main.rs:143-150).  That table
+ * cannot exist on a GPU design, so this boundary fuses the two calls: inputs are the first two
+ * sequences as bytes + Scores + is_local, the output is the content of AlignedSequences
+ * (algo.rs:135-146).  Results are bit-identical to the reference for every input that satisfies
+ * the preconditions checked by gx_check_scores() -- including the reference's non-textbook
+ * tie-breaks.  There is no CPU fallback: every entry point fails with
+ * GX_ERR_NO_DEVICE / GX_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Plain C, plain pointers and sizes; the library owns all device memory and pinned staging.
+ * Calls on one context are serialised internally; callers may be multi-threaded.
+ * The library never writes to stdout/stderr and never throws or aborts across the ABI.
+ */
+#ifndef GXALIGN_H
+#define GXALIGN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (replace the reference's panic!/exit(1): algo.rs:168-169,407-408; config.rs:26,34) */
+enum {
+    GX_OK = 0,
+    GX_ERR_ARG = 1,           /* null pointer / inconsistent sizes */
+    GX_ERR_SCORES = 2,        /* precondition violated: need h <= 0, g < 0, h+g < 0 */
+    GX_ERR_RANGE = 3,         /* (m+n+2)*max|score| + |h| >= 2^29: int32 cell state would overflow */
+    GX_ERR_OPS_CAP = 4,       /* ops buffer too small (need >= m+n+1) */
+    GX_ERR_NO_DEVICE = 5,     /* no CUDA device of compute capability 10.x; there is no CPU path */
+    GX_ERR_CUDA = 6,          /* CUDA runtime error, see gx_last_error() */
+    GX_ERR_NOMEM = 7,         /* device or host allocation failed / traceback storage would not fit */
+    GX_ERR_NOT_INIT = 8,      /* gx_init() has not been called */
+    GX_ERR_UNSUPPORTED = 9,   /* flag or mode not implemented */
+    GX_ERR_INTERNAL = 10      /* impossible traceback state (the reference panics: algo.rs:407-408) */
+};
+
+/* ---- Scores: /root/reference/src/config.rs:6-13 (i64 there; int32 here, range-checked) */
+typedef struct gx_scores {
+    int32_t s_match;
+    int32_t s_mismatch;
+    int32_t g;   /* gap extension, per gap column (negative) */
+    int32_t h;   /* gap opening (non-positive) */
+} gx_scores;
+
+/* ---- AlignmentChoice discriminants: algo.rs:124-133 (#[repr(u8)]) */
+enum {
+    GX_MATCH = 0, GX_MISMATCH = 1, GX_INSERT = 2, GX_DELETE = 3, GX_OPEN_INSERT = 4, GX_OPEN_DELETE = 5
+};
+
+/* ---- flags */
+enum {
+    GX_FLAG_TRACEBACK = 1,    /* fill direction codes and walk them (retrace, algo.rs:287-441) */
+    GX_FLAG_LCS_AT_MAX = 2,   /* also return alignment_table's 2nd value (algo.rs:279-281) -- not implemented yet */
+    GX_FLAG_START_CELL = 4    /* score-only local: also report the start cell (last argmax, algo.rs:311-322) */
+};
+
+/* ---- AlignedSequences minus the sequence clones: algo.rs:135-146.
+ * ops[k] is the AlignmentChoice discriminant of alignment[k] (walk order, start cell first,
+ * algo.rs:357-396); the (i,j) of each entry follows by replaying the moves from (start_i,start_j)
+ * with the checked_sub rules of algo.rs:412-417 (gx_replay_ops does it). */
+typedef struct gx_result {
+    int64_t score;            /* AlignedSequences.score, algo.rs:331 */
+    uint64_t start_i, start_j;/* first walked cell: (m,n) global; last-argmax local (algo.rs:306-323) */
+    uint64_t end_i, end_j;    /* last emitted cell */
+    uint64_t n_ops;           /* alignment.len() */
+    uint64_t matches, mismatches, gap_extensions, opening_gaps; /* algo.rs:141-145 */
+    uint64_t lcs_at_first_max;/* GX_FLAG_LCS_AT_MAX only */
+    double fill_ms, walk_ms;  /* device time of the fill / walk kernels of the call (shared by a batch) */
+} gx_result;
+
+/* ---- lifecycle.  One context per process, bound to one device (one process per GPU). */
+int gx_init(int device);            /* device ordinal, or -1 for the current device */
+void gx_shutdown(void);
+int gx_device_count(void);          /* number of usable sm_100 devices, 0 if none / no driver */
+const char *gx_strerror(int status);
+const char *gx_last_error(void);    /* detail of the last GX_ERR_CUDA on this thread's context */
+const char *gx_version(void);
+
+/* GX_OK iff the reference's results can be reproduced in int32 for these lengths. */
+int gx_check_scores(gx_scores sc, uint64_t m, uint64_t n);
+
+/* ---- one pair, host buffers in, host buffers out.   replaces alignment_table + retrace.
+ * s1 = sequences[0] (rows, i), s2 = sequences[1] (columns, j); any byte values.
+ * ops may be NULL when GX_FLAG_TRACEBACK is not set; otherwise ops_cap >= m+n+1. */
+int gx_align_pair(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n,
+                  gx_scores sc, int is_local, int flags,
+                  gx_result *out, uint8_t *ops, uint64_t ops_cap);
+
+/* ---- many independent pairs in one call (pairs scattered over the SMs of this context's GPU).
+ * Pair p is seq_blob[off1[p] .. off1[p]+len1[p]) vs seq_blob[off2[p] .. off2[p]+len2[p]).
+ * With GX_FLAG_TRACEBACK pair p's ops go to ops_blob[ops_off[p] ..] and ops_off must have n_pairs+1
+ * entries with ops_off[p+1]-ops_off[p] >= len1[p]+len2[p]+1. */
+int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len,
+                   const uint64_t *off1, const uint64_t *len1,
+                   const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs,
+                   gx_scores sc, int is_local, int flags,
+                   gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off);
+
+/* ---- score-only batch (no traceback, no start cell): the form the short-read workload uses
+ * (BASELINE config 4: 10M x 150 bp local).  Pairs of up to 640 bp run on the inter-task kernel. */
+int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len,
+                   const uint64_t *off1, const uint64_t *len1,
+                   const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs,
+                   gx_scores sc, int is_local, int64_t *scores);
+
+/* ---- the same, split into phases so that callers can keep inputs resident in HBM, overlap
+ * copies, and time the kernels alone.  gx_align_batch == create + upload + execute + fetch + destroy. */
+typedef struct gx_plan gx_plan;
+int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
+                   gx_scores sc, int is_local, int flags, gx_plan **plan);
+int gx_plan_upload(gx_plan *plan, const uint8_t *seq_blob, uint64_t blob_len,
+                   const uint64_t *off1, const uint64_t *off2);            /* host -> HBM */
+int gx_plan_execute(gx_plan *plan);                                        /* kernels only, synchronous */
+int gx_plan_fetch(gx_plan *plan, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off); /* HBM -> host */
+int gx_plan_fetch_scores(gx_plan *plan, int64_t *scores);   /* scores only: 4 B per pair on the wire for read batches */
+void gx_plan_destroy(gx_plan *plan);
+/* introspection for benchmarks: what==0 fill ms, 1 walk ms, 2 kernels launched by the last execute,
+ * 3 cells (sum (m+1)(n+1)), 4 traceback bytes written per execute, 5 device bytes held by the plan,
+ * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch) */
+double gx_plan_stat(const gx_plan *plan, int what);
+
+/* ---- replay helper: expands ops into (i,j) per entry exactly as algo.rs:412-417 would have pushed them. */
+int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t start_j,
+                  uint32_t *ops_i, uint32_t *ops_j);
+
+/* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator, SURVEY.md 8d "K0").
+ * Fills out[0..n) with warp-instructions per clock per SM for:
+ * 0 IADD3, 1 VIADDMNMX, 2 VIMNMX3, 3 ISETP+SEL, 4 IMAD, 5 the 7-op NW cell mix (cells/clk/SM),
+ * 6 SM clock MHz observed, 7 SM count.  Returns the number of entries written or a negative status. */
+int gx_k0_measure(double *out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GXALIGN_H */

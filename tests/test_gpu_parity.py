@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-shaped host mirror) against the
+oracle and the committed golden vectors.  Integer work: every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import CONFIG_TOML, TEST_CONFIG, random_pair, read_fasta_gz
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gx():
+    import genomics_rs_b200 as gx
+    from genomics_rs_b200 import _lib
+    _lib.ensure_init()
+    return gx
+
+
+def _container(gx, s1, s2):
+    return gx.SequenceContainer(sequences=[gx.Sequence("s1", s1), gx.Sequence("s2", s2)])
+
+
+def _same(gpu, ora, oracle, what=""):
+    assert gpu.score == ora.score, what
+    assert tuple(gpu.start) == tuple(ora.start), what
+    assert tuple(gpu.end) == tuple(ora.end), what
+    assert (gpu.matches, gpu.mismatches, gpu.gap_extensions, gpu.opening_gaps) == (
+        ora.matches, ora.mismatches, ora.gap_extensions, ora.opening_gaps), what
+    assert np.array_equal(gpu.ops, ora.ops), what
+    oi, oj = gpu.coords()
+    assert np.array_equal(oi, ora.ops_i) and np.array_equal(oj, ora.ops_j), what
+
+
+# ---- the reference's own tests (tests/test_alignment.rs:23-139), written the way the reference writes them
+def test_reference_test_simple_matches(gx):
+    sc = _container(gx, "ACGT", "ACGT")
+    scores = gx.Scores(1, -2, -2, -5)
+    table, _ = gx.alignment_table(sc, scores, False, False)
+    aligned = gx.retrace(sc, table, False)
+    M = gx.AlignmentChoice.Match
+    assert aligned.score == 4
+    assert (aligned.matches, aligned.mismatches, aligned.opening_gaps, aligned.gap_extensions) == (4, 0, 0, 0)
+    assert aligned.alignment == [(M, 4, 4), (M, 3, 3), (M, 2, 2), (M, 1, 1)]
+
+
+def test_reference_test_gaps(gx):
+    sc = _container(gx, "ACGT", "AGCGT")
+    table, _ = gx.alignment_table(sc, gx.Scores(1, -2, -2, -5), False, False)
+    aligned = gx.retrace(sc, table, False)
+    C = gx.AlignmentChoice
+    assert (aligned.matches, aligned.mismatches, aligned.opening_gaps, aligned.gap_extensions) == (3, 1, 1, 0)
+    assert aligned.alignment == [(C.Match, 4, 5), (C.Match, 3, 4), (C.Match, 2, 3), (C.OpenInsert, 1, 2), (C.Mismatch, 1, 1)]
+    assert str(aligned).startswith("\n\n0-5:\n\nA-CGT\nx%|||\nAGCGT\n")
+
+
+def test_reference_test_affine_gap(gx, ref_vectors):
+    case = ref_vectors["cases"][2]
+    sc = _container(gx, case["s1"], case["s2"])
+    table, _ = gx.alignment_table(sc, gx.Scores(1, -2, -2, -5), False, False)
+    aligned = gx.retrace(sc, table, False)
+    assert (aligned.matches, aligned.mismatches, aligned.opening_gaps, aligned.gap_extensions) == (12, 0, 1, 3)
+    assert [[c.name, i, j] for c, i, j in aligned.alignment] == case["alignment"]
+
+
+# ---- fixtures vs committed goldens and vs the oracle, global and local (configs 1 and 2 of BASELINE.json)
+@pytest.mark.parametrize("fixture", ["test1", "test2_short", "test3_short", "test4", "Opsin1_colorblindness_gene",
+                                     "Human-Mouse-BRCA2-cds"])
+@pytest.mark.parametrize("is_local", [False, True])
+def test_fixture_parity(gx, oracle, goldens, fixture, is_local):
+    g = next(p for p in goldens["pairs"] if p["fixture"] == fixture and p["is_local"] == is_local)
+    s = read_fasta_gz(fixture)
+    sc = gx.SequenceContainer(sequences=[gx.Sequence(*s[0]), gx.Sequence(*s[1])])
+    a = gx.align(sc, gx.Scores(*CONFIG_TOML), is_local)
+    assert a.score == g["score"] and list(a.start) == g["start"] and list(a.end) == g["end"]
+    assert len(a.ops) == g["n_ops"]
+    assert (a.matches, a.mismatches, a.gap_extensions, a.opening_gaps) == (
+        g["matches"], g["mismatches"], g["gap_extensions"], g["opening_gaps"])
+    assert "%016x" % oracle.hash_ops(a.ops, a.start) == g["op_hash"]
+    o = oracle.align_linear(s[0][1], s[1][1], CONFIG_TOML, is_local)
+    _same(a, o, oracle, fixture)
+
+
+def test_edge_cases(gx, oracle):
+    cases = [("", ""), ("", "ACG"), ("ACG", ""), ("A", "A"), ("A", "C"), ("AAAA", "TTTT"), ("ACGT" * 70, "ACGT" * 70),
+             ("A" * 257, "A" * 256), ("ACGTTGCA" * 40, "TTTT"), ("G", "ACGT" * 100), ("\x00\xff\x80A", "\x00\xffA\x80")]
+    for scores in (CONFIG_TOML, TEST_CONFIG, (2, 1, -1, 0)):
+        for is_local in (False, True):
+            pairs = [(a.encode("latin-1"), b.encode("latin-1")) for a, b in cases]
+            got = gx.align_batch(pairs, scores, is_local)
+            for (a, b), r in zip(pairs, got):
+                o = oracle.align_faithful(a, b, scores, is_local)
+                _same(r, o, oracle, f"{a[:12]!r} {b[:12]!r} {scores} local={is_local}")
+
+
+@pytest.mark.parametrize("scores", [CONFIG_TOML, TEST_CONFIG, (2, -1, -1, 0), (5, -4, -3, -10), (1, 0, -1, -1), (3, 1, -2, -2)])
+def test_random_small_vs_faithful(gx, oracle, scores):
+    rng = np.random.default_rng(hash(scores) & 0xffff)
+    pairs = []
+    for _ in range(200):
+        m, n = int(rng.integers(0, 70)), int(rng.integers(0, 70))
+        pairs.append(random_pair(rng, m, n, alphabet=b"ACGT" if rng.random() < 0.7 else b"AC", similar=bool(rng.integers(0, 2))))
+    for is_local in (False, True):
+        got = gx.align_batch(pairs, scores, is_local)
+        for (a, b), r in zip(pairs, got):
+            o = oracle.align_faithful(a, b, scores, is_local)
+            _same(r, o, oracle, f"m={len(a)} n={len(b)} {scores} local={is_local}")
+
+
+def test_random_medium_ragged_vs_linear(gx, oracle):
+    """sizes that cross strip (256 columns), block (32 rows) and panel (4096 rows) boundaries"""
+    rng = np.random.default_rng(11)
+    dims = [(255, 256), (256, 257), (257, 255), (31, 600), (33, 1025), (1000, 31), (513, 513), (4095, 300), (4096, 300),
+            (4097, 300), (4200, 520), (300, 4200), (8193, 770), (1, 3000), (3000, 1)]
+    pairs = [random_pair(rng, m, n, similar=(k % 3 != 0)) for k, (m, n) in enumerate(dims)]
+    for is_local in (False, True):
+        got = gx.align_batch(pairs, CONFIG_TOML, is_local)
+        for (a, b), r in zip(pairs, got):
+            o = oracle.align_linear(a, b, CONFIG_TOML, is_local)
+            _same(r, o, oracle, f"m={len(a)} n={len(b)} local={is_local}")
+
+
+def test_score_only_and_start_cell(gx, oracle):
+    rng = np.random.default_rng(5)
+    pairs = [random_pair(rng, int(rng.integers(1, 900)), int(rng.integers(1, 900))) for _ in range(40)]
+    for is_local in (False, True):
+        got = gx.align_batch(pairs, CONFIG_TOML, is_local, traceback=False, start_cell=True)
+        for (a, b), r in zip(pairs, got):
+            sc, si, sj = oracle.score_linear(a, b, CONFIG_TOML, is_local)
+            assert r.score == sc and tuple(r.start) == (si, sj)
+        got = gx.align_batch(pairs, CONFIG_TOML, is_local, traceback=False)
+        for (a, b), r in zip(pairs, got):
+            assert r.score == oracle.score_linear(a, b, CONFIG_TOML, is_local)[0]
+
+
+def test_plan_reexecute_is_idempotent(gx, oracle):
+    """the LL parity protocol must survive repeated executes of one plan (bench.py re-runs plans)"""
+    rng = np.random.default_rng(9)
+    pairs = [random_pair(rng, 1500, 1300), random_pair(rng, 700, 2100)]
+    blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+    plan = gx.Plan(len1, len2, CONFIG_TOML, False, traceback=True)
+    plan.upload(blob, off1, off2)
+    ref = None
+    for _ in range(5):
+        plan.execute()
+        res, ops, ops_off = plan.fetch()
+        cur = (res["score"].tolist(), res["n_ops"].tolist(), ops.tobytes())
+        if ref is None:
+            ref = cur
+            for q, (a, b) in enumerate(pairs):
+                o = oracle.align_linear(a, b, CONFIG_TOML, False)
+                assert res["score"][q] == o.score
+                k = int(res["n_ops"][q])
+                assert np.array_equal(ops[int(ops_off[q]):int(ops_off[q]) + k], o.ops)
+        assert cur == ref
+    plan.close()
+
+
+def test_corona_all_vs_all(gx, oracle, goldens):
+    """BASELINE config 3: 45 pairs of ~30 kb genomes, global, score + traceback, one batch."""
+    order = goldens["corona_order"]
+    seqs = [read_fasta_gz(name)[0][1] for name in order]
+    jobs = [(a, b) for a in range(len(seqs)) for b in range(a + 1, len(seqs))]
+    got = gx.align_batch([(seqs[a], seqs[b]) for a, b in jobs], CONFIG_TOML, False)
+    gold = {tuple(c["pair"]): c for c in goldens["corona"]}
+    for (a, b), r in zip(jobs, got):
+        g = gold[(a, b)]
+        assert r.score == g["score"], (a, b)
+        assert len(r.ops) == g["n_ops"], (a, b)
+        assert (r.matches, r.mismatches, r.gap_extensions, r.opening_gaps) == (
+            g["matches"], g["mismatches"], g["gap_extensions"], g["opening_gaps"]), (a, b)
+        assert "%016x" % oracle.hash_ops(r.ops, r.start) == g["op_hash"], (a, b)
+
+
+def test_read_batch_scores(gx, oracle):
+    """BASELINE config 4 shape: many 150 bp pairs, local score only (inter-task kernel), plus ragged lengths."""
+    rng = np.random.default_rng(150)
+    n_pairs = 20000
+    pairs = [random_pair(rng, 150, 150, similar=(k % 4 != 0), sub=0.06, indel=0.01) for k in range(n_pairs)]
+    blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+    for is_local in (True, False):
+        got = gx.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, is_local)
+        exp = oracle.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, is_local, n_threads=8)
+        assert np.array_equal(got, exp)
+    ragged = [random_pair(rng, int(rng.integers(0, 152)), int(rng.integers(0, 152))) for _ in range(5000)]
+    ragged += [random_pair(rng, int(rng.integers(100, 600)), int(rng.integers(100, 600))) for _ in range(1500)]
+    blob, off1, len1, off2, len2 = gx.pack_pairs(ragged)
+    for is_local in (True, False):
+        got = gx.score_batch(blob, off1, len1, off2, len2, TEST_CONFIG, is_local)
+        exp = oracle.score_batch(blob, off1, len1, off2, len2, TEST_CONFIG, is_local, n_threads=8)
+        assert np.array_equal(got, exp)
+
+
+def test_large_properties(gx, oracle):
+    """size-independent properties at sizes the oracle does not brute-force:
+    identical sequences give m*match with an all-Match walk; transposing the pair (I <-> D) keeps the
+    global and the local score; a substitution-only pair agrees with the oracle's score."""
+    rng = np.random.default_rng(77)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    m = 60000
+    a = lut[rng.integers(0, 4, size=m)]
+    r = gx.align_batch([(a, a)], CONFIG_TOML, False)[0]
+    assert r.score == m and r.matches == m and len(r.ops) == m and r.end == (1, 1)
+    assert not r.ops.any()
+    A, B = random_pair(rng, 50000, 48000, sub=0.1, indel=0.02)
+    for is_local in (False, True):
+        x = gx.align_batch([(A, B), (B, A)], CONFIG_TOML, is_local, traceback=False)
+        assert x[0].score == x[1].score
+    a4 = rng.integers(0, 4, size=20000)
+    b4 = a4.copy()
+    idx = rng.choice(20000, size=600, replace=False)
+    b4[idx] = (b4[idx] + 1 + rng.integers(0, 3, size=600)) % 4
+    r = gx.align_batch([(lut[a4], lut[b4])], CONFIG_TOML, False)[0]
+    assert r.score == oracle.score_linear(lut[a4], lut[b4], CONFIG_TOML, False)[0]
