@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the affine-gap NW/SW hot path on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload corona45|brca2_global|brca2_local|reads150]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
+
+A "step" is one pass of the hot path over the workload's batch of pairs:
+  value      kernels only, sequences resident in HBM (gx_plan_execute), device-timed with CUDA events
+  e2e        the public host-buffer call (gx_align_batch / gx_score_batch): H2D + kernels + D2H, wall clock
+Metric: GCUPS = sum (m+1)(n+1) / seconds / 1e9 (cells of the reference's table, algo.rs:172).
+torch is used for process-group plumbing (rendezvous, barrier, max over ranks) and pinned host buffers only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from genomics_rs_b200 import workloads as wl  # noqa: E402
+
+SCORES = wl.CONFIG_TOML
+OPS_PER_CELL = {"global_score": 7, "local_score": 8, "traceback": 13}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d.get("hbm_gbs", 6650.0)), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(name: str, rank: int, world: int, n_pairs: int):
+    """-> dict(blob, off1, len1, off2, len2, is_local, traceback, cells, desc, scaling, mode)"""
+    if name == "corona45":
+        seqs, jobs = wl.corona_pairs()
+        costs = [(len(seqs[a]) + 1) * (len(seqs[b]) + 1) for a, b in jobs]
+        mine = wl.lpt_shards(costs, world)[rank]
+        off, pos = [], 0
+        for s in seqs:
+            off.append(pos); pos += len(s)
+        blob = np.frombuffer(b"".join(seqs), np.uint8).copy()
+        off1 = np.array([off[jobs[k][0]] for k in mine], np.uint64)
+        off2 = np.array([off[jobs[k][1]] for k in mine], np.uint64)
+        len1 = np.array([len(seqs[jobs[k][0]]) for k in mine], np.uint64)
+        len2 = np.array([len(seqs[jobs[k][1]]) for k in mine], np.uint64)
+        return dict(blob=blob, off1=off1, len1=len1, off2=off2, len2=len2, is_local=False, traceback=True,
+                    cells=int(sum(costs[k] for k in mine)), scaling="strong", mode="traceback",
+                    desc="config 3: all-vs-all global NW of the 10 comparison_data coronavirus genomes (45 pairs, ~30 kb each), "
+                         "score + traceback, pairs dealt LPT over ranks")
+    if name in ("brca2_global", "brca2_local"):
+        a, b = wl.brca2_pair()
+        blob = np.frombuffer(a + b, np.uint8).copy()
+        is_local = name.endswith("local")
+        return dict(blob=blob, off1=np.array([0], np.uint64), len1=np.array([len(a)], np.uint64),
+                    off2=np.array([len(a)], np.uint64), len2=np.array([len(b)], np.uint64), is_local=is_local, traceback=True,
+                    cells=(len(a) + 1) * (len(b) + 1), scaling="weak", mode="traceback",
+                    desc=f"config {'2' if is_local else '1'}: {'local SW' if is_local else 'global NW'} of "
+                         "Human-Mouse-BRCA2-cds (11382 x 10346), score + traceback; one pair per rank (replicas)")
+    if name == "reads150":
+        per = n_pairs // world
+        first = rank * per
+        blob, off1, len1, off2, len2 = wl.reads150(first, per)
+        return dict(blob=blob, off1=off1, len1=len1, off2=off2, len2=len2, is_local=True, traceback=False,
+                    cells=per * 151 * 151, scaling="strong", mode="local_score",
+                    desc=f"config 4: {n_pairs} synthetic 150 bp pairs (splitmix64), local SW score only, contiguous ranges per rank")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def pinned_like(arr: np.ndarray):
+    """copy into page-locked host memory (torch owns the allocation; numpy view for ctypes)"""
+    import torch
+    t = torch.empty(arr.size, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    v = t.numpy()
+    v[:] = arr.view(np.uint8).reshape(-1)
+    return t, v
+
+
+def cpu_baseline_sample(march_native: bool = True, rows: int = 12000, threads: int = 1):
+    """The reference's algorithm as written (oracle faithful variant: 48 B cells, F-order table, i-outer/j-inner)
+    on a bounded sample of the workload: the first `rows` x `rows` bases of corona pair (0,1), global + retrace."""
+    from oracle import gxo
+    so = gxo.build(march="native") if march_native else None
+    seqs, jobs = wl.corona_pairs()
+    a, b = seqs[0][:rows], seqs[1][:rows]
+    cells = (len(a) + 1) * (len(b) + 1)
+    t0 = time.perf_counter()
+    r = gxo.align_faithful(a, b, SCORES, False, so=so)
+    dt = time.perf_counter() - t0
+    return dict(value=cells / dt / 1e9, unit="GCUPS", cores=threads, kind="port",
+                sample=f"oracle faithful variant (48 B cells, column-major, single thread like algo.rs), global NW + retrace of the "
+                       f"first {rows}x{rows} bases of corona pair (Covid_Australia, Covid_Brazil): {cells} cells in {dt:.2f} s "
+                       f"(fill {r.fill_ms / 1e3:.2f} s)",
+                seconds=dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate cannot be built
+    here) on the host cores.  The reference aligns ONE pair on ONE thread (no rayon in algo.rs); to use the host
+    it is run as T independent single-threaded aligners, one bounded-sample pair each, per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import gxo
+    so = gxo.build(march="native")
+    ncpu = os.cpu_count() or 1
+    threads = max(1, min(ncpu, 32))
+    rows = 4000
+    seqs, jobs = wl.corona_pairs()
+    work = [(seqs[a][:rows], seqs[b][:rows]) for a, b in jobs]
+    work = (work * ((threads + len(work) - 1) // len(work)))[:threads]
+    cells = sum((len(a) + 1) * (len(b) + 1) for a, b in work)
+
+    def one(ab):
+        return gxo.align_faithful(ab[0], ab[1], SCORES, False, so=so).score   # ctypes releases the GIL
+
+    def step():
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, work))
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = cells / dt / 1e9
+    sample = (f"{threads} concurrent single-threaded aligners (reference algorithm as written, 48 B cells), each the first "
+              f"{rows}x{rows} bases of a corona pair, global NW + retrace; {cells} cells per step")
+    print(json.dumps({
+        "impl": "reference", "metric": "GCUPS (affine NW/SW, score+traceback)", "value": val, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "reference fixtures (comparison_data genomes, prefixes)",
+        "config": {"workload": "corona45 (bounded sample, CPU)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="corona45")
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="reads150: total pairs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-k0", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libgxalign has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import genomics_rs_b200 as gx
+    from genomics_rs_b200 import _lib
+    _lib.ensure_init(local_rank)
+
+    w = build_workload(args.workload, rank, world, args.pairs)
+    pin_t, blob = pinned_like(w["blob"])
+    plan = gx.Plan(w["len1"], w["len2"], SCORES, w["is_local"], traceback=w["traceback"])
+    plan.upload(blob, w["off1"], w["off2"])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    k0 = None
+    if rank == 0 and not args.no_k0:
+        k0 = gx.k0_measure()
+
+    # ---- kernels only (HBM resident)
+    for _ in range(args.warmup):
+        plan.execute()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    dev_ms, fill_ms, walk_ms, launches = 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.execute()
+        fill_ms += plan.fill_ms
+        walk_ms += plan.walk_ms
+        launches += plan.launches
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    dev_ms = fill_ms + walk_ms
+
+    # ---- end to end: host buffers in, host buffers out, through the public batch call
+    n = int(w["len1"].size)
+    if w["traceback"]:
+        res = np.zeros(n, dtype=gx.RESULT_DTYPE)
+        ops_off = np.zeros(n + 1, np.uint64)
+        np.cumsum(w["len1"] + w["len2"] + np.uint64(1), out=ops_off[1:])
+        ops_t = torch.empty(int(ops_off[-1]), dtype=torch.uint8, pin_memory=True)
+        ops = ops_t.numpy()
+        lib = _lib.load()
+        sc = _lib.GxScores(*SCORES)
+
+        def e2e_step():
+            _lib.check(lib.gx_align_batch(blob.ctypes.data, blob.size, w["off1"].ctypes.data, w["len1"].ctypes.data,
+                                          w["off2"].ctypes.data, w["len2"].ctypes.data, n, sc, int(w["is_local"]),
+                                          _lib.GX_FLAG_TRACEBACK, res.ctypes.data, ops.ctypes.data, ops_off.ctypes.data))
+        d2h = n * gx.RESULT_DTYPE.itemsize + int(res_bytes_hint(w))
+    else:
+        scores_out = np.zeros(n, np.int64)
+
+        def e2e_step():
+            scores_out[:] = gx.score_batch(blob, w["off1"], w["len1"], w["off2"], w["len2"], SCORES, w["is_local"])
+        d2h = n * 4
+    h2d = int(blob.size) + (n * 16 if not w["traceback"] else n * 80)
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # ---- max over ranks, totals over ranks
+    vals = torch.tensor([dev_ms / args.steps, wall_ms / args.steps, e2e_ms, fill_ms / args.steps, walk_ms / args.steps],
+                        dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(w["cells"]), float(launches), float(h2d), float(d2h), float(plan.stat(4))],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, wall_step, e2e_step_ms, fill_step, walk_step = [float(x) for x in vals.tolist()]
+    cells, launches_all, h2d_all, d2h_all, code_bytes = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = cells / (ms_step * 1e-3) / 1e9
+        e2e_val = cells / (e2e_step_ms * 1e-3) / 1e9
+        ops_cell = OPS_PER_CELL[w["mode"] if w["mode"] != "local_score" else "local_score"]
+        sms = int(k0["sm_count"]) if k0 else 148
+        lanes = 64.0   # INT32 ALU lanes per clock per SM; K0 below reports what this chip actually issues
+        peak_tops = sms * lanes * peaks["sm_max_mhz"] * 1e6 / 1e12
+        # the dominant kernel is the fill; its per-launch duration is the event-timed fill span of this rank
+        my_cells = float(w["cells"])
+        achieved_tops = my_cells * ops_cell / (fill_ms / args.steps * 1e-3) / 1e12
+        roof = {"bound": "int32-alu", "kernel": "gx_fill_kernel" if plan.stat(9) == 0 else "gx_reads_kernel",
+                "achieved": achieved_tops, "peak": peak_tops, "unit": "Tinstr-lanes/s (int32 ops/s /1e12)",
+                "frac": achieved_tops / peak_tops, "ops_per_cell": ops_cell,
+                "peak_basis": f"{sms} SMs x {lanes:.0f} INT32 lanes/clk x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
+                "gcups_kernel": my_cells / (fill_ms / args.steps * 1e-3) / 1e9,
+                "traffic": None}
+        hbm = None
+        if w["traceback"]:
+            gbs = float(plan.stat(4)) / (fill_ms / args.steps * 1e-3) / 1e9
+            hbm = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                   "what": "traceback codes written once per cell (0.25 B/cell)", "peak_source": peaks["source"]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline_sample()
+        line = {
+            "metric": "GCUPS (affine NW/SW, score+traceback)" if w["traceback"] else "GCUPS (affine SW, score only)",
+            "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "int32", "data": "reference fixtures (tests/golden/fasta, gz copies of comparison_data/test_data)"
+            if args.workload != "reads150" else "synthetic (splitmix64 reads, SURVEY 8d)",
+            "config": {"workload": args.workload, "what": w["desc"], "scores": dict(zip(("s_match", "s_mismatch", "g", "h"), SCORES)),
+                       "cells_per_step": cells, "l2": "each step rewrites %.2f GB of traceback codes + boundary buffers, far above the "
+                       "126 MB L2, so no step sees a warm cache" % (code_bytes / 1e9) if w["traceback"] else
+                       "inputs (%.2f GB) exceed L2" % (blob.size * world / 1e9)},
+            "wall_ms_per_step": wall_step, "fill_ms_per_step": fill_step, "walk_ms_per_step": walk_step,
+            "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_step_ms, "h2d_bytes_per_step": h2d_all,
+                    "d2h_bytes_per_step": d2h_all, "api": "gx_align_batch" if w["traceback"] else "gx_score_batch"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks, "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "k0": k0,
+        }
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def res_bytes_hint(w):
+    return int((w["len1"] + w["len2"] + np.uint64(1)).sum())
+
+
+if __name__ == "__main__":
+    main()

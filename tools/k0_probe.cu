@@ -1,0 +1,90 @@
+// k0_probe.cu -- standalone issue-rate probe for the INT32/DPX instruction forms the DP kernels use.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o k0_probe k0_probe.cu ; run on a B200.
+// Each variant is an unrolled dependency-free set of CH chains per thread; rate = warp-instr/clk/SM.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+constexpr int ITERS = 2048;
+#define CH 12
+
+template <int OP>
+__global__ void __launch_bounds__(256) probe(int *sink, long long *cycles, int seed) {
+    int v[CH], w[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { v[c] = seed + threadIdx.x * 7 + c; w[c] = seed * 3 + c * 5 + threadIdx.x; }
+    const int g = seed - 3, hg = seed - 9;
+    float f[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) f[c] = (float)v[c];
+    const float fa = (float)seed * 0.5f, fb = (float)seed;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (OP == 0) asm volatile("add.s32 %0, %0, 7;" : "+r"(v[c]));                                   // imm add
+            if (OP == 1) asm volatile("add.s32 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));                        // 2-reg add
+            if (OP == 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[c]) : "r"(w[c]), "r"(g));     // 3-reg lop3
+            if (OP == 3) asm volatile("lop3.b32 %0, %0, 0x55aa, %1, 0x96;" : "+r"(v[c]) : "r"(g));            // lop3 imm
+            if (OP == 4) v[c] = __viaddmax_s32(v[c], g, w[c]);                                                // VIADDMNMX r,r(shared),r
+            if (OP == 5) v[c] = __viaddmax_s32(v[c], -1, w[c]);                                               // VIADDMNMX r,imm,r
+            if (OP == 6) v[c] = __vimax3_s32(v[c], w[c], g);                                                  // VIMNMX3 3-reg
+            if (OP == 7) v[c] = max(v[c], w[c]);                                                              // VIMNMX 2-reg
+            if (OP == 8) asm volatile("mad.lo.s32 %0, %0, 3, %1;" : "+r"(v[c]) : "r"(w[c]));                  // IMAD imm
+            if (OP == 9) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(fa), "f"(fb));          // FFMA 3-reg
+            if (OP == 10) { asm volatile("add.s32 %0, %0, 7;" : "+r"(v[c])); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[c]) : "f"(fa), "f"(fb)); }  // ALU+FMA pair
+            if (OP == 11) { v[c] = __viaddmax_s32(v[c], -1, w[c]); asm volatile("mad.lo.s32 %0, %0, 3, %1;" : "+r"(w[c]) : "r"(g)); }                          // DPX + IMAD pair
+            if (OP == 12) { v[c] = (v[c] == w[c]) ? g : hg; }                                                 // ISETP + SEL
+            if (OP == 13) { v[c] = __viaddmax_s32(v[c], -1, w[c]); w[c] = __viaddmax_s32(w[c], -1, v[c]); }   // 2 DPX dependent pair
+            if (OP == 14) asm volatile("vadd.s32.s32.s32 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+        }
+    }
+    const long long t1 = clock64();
+    int acc = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc ^= v[c] ^ w[c] ^ __float_as_int(f[c]);
+    if (acc == 0x7fffffff) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char *name, int per_iter, int sms, int *sink, long long *cyc) {
+    for (int cps = 1; cps <= 4; cps *= 2) {
+        const int grid = sms * cps;
+        probe<OP><<<grid, 256>>>(sink, cyc, 11);
+        probe<OP><<<grid, 256>>>(sink, cyc, 13);
+        cudaDeviceSynchronize();
+        long long *h = new long long[grid];
+        cudaMemcpy(h, cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+        double avg = 0;
+        for (int k = 0; k < grid; ++k) avg += (double)h[k];
+        avg /= grid;
+        delete[] h;
+        const double winstr = (double)ITERS * CH * per_iter * 8 * cps;
+        printf("%-34s warps/SM=%2d  %.3f warp-instr/clk/SM  (%.1f lanes/clk/SM)\n", name, 8 * cps, winstr / avg, 32 * winstr / avg);
+    }
+}
+
+int main() {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int *sink; long long *cyc;
+    cudaMalloc(&sink, 64); cudaMalloc(&cyc, sizeof(long long) * sms * 8);
+    run<0>("IADD imm", 1, sms, sink, cyc);
+    run<1>("IADD 2-reg", 1, sms, sink, cyc);
+    run<2>("LOP3 3-reg", 1, sms, sink, cyc);
+    run<3>("LOP3 imm", 1, sms, sink, cyc);
+    run<4>("VIADDMNMX r,r,r", 1, sms, sink, cyc);
+    run<5>("VIADDMNMX r,imm,r", 1, sms, sink, cyc);
+    run<6>("VIMNMX3 r,r,r", 1, sms, sink, cyc);
+    run<7>("VIMNMX r,r", 1, sms, sink, cyc);
+    run<8>("IMAD r,imm,r", 1, sms, sink, cyc);
+    run<9>("FFMA r,r,r", 1, sms, sink, cyc);
+    run<10>("IADD imm + FFMA", 2, sms, sink, cyc);
+    run<11>("VIADDMNMX imm + IMAD", 2, sms, sink, cyc);
+    run<12>("ISETP+SEL", 2, sms, sink, cyc);
+    run<13>("2x VIADDMNMX imm (dep pair)", 2, sms, sink, cyc);
+    printf("done %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
