@@ -124,6 +124,9 @@ struct gx_plan {
     uint64_t max_len = 0;
     // device
     uint8_t *d_blob = nullptr;
+    uint8_t *d_blob_sym = nullptr;     // blob re-encoded to symbols 0..3 when the batch uses <= 4 distinct bytes
+    uint8_t *d_lut = nullptr;
+    bool prof = false;
     gx::PairDesc *d_pairs = nullptr;
     gx::TileDesc *d_tiles = nullptr;
     uint32_t *d_ctrl = nullptr;  // [0] ticket, [16..] progress
@@ -153,11 +156,19 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
     const size_t smem = (size_t)WARPS_PER_CTA * WARP_SMEM;
     void (*kern)(const FillParams) = nullptr;
     const bool L = pl->is_local != 0, C = pl->traceback;
-    if (!L && !C) kern = gx_fill_kernel<K, false, false, 0>;
-    else if (!L && C) kern = gx_fill_kernel<K, false, true, 0>;
-    else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1>;
-    else if (L && !C) kern = gx_fill_kernel<K, true, false, 2>;
-    else kern = gx_fill_kernel<K, true, true, 2>;
+    if (pl->prof) {
+        if (!L && !C) kern = gx_fill_kernel<K, false, false, 0, true>;
+        else if (!L && C) kern = gx_fill_kernel<K, false, true, 0, true>;
+        else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1, true>;
+        else if (L && !C) kern = gx_fill_kernel<K, true, false, 2, true>;
+        else kern = gx_fill_kernel<K, true, true, 2, true>;
+    } else {
+        if (!L && !C) kern = gx_fill_kernel<K, false, false, 0, false>;
+        else if (!L && C) kern = gx_fill_kernel<K, false, true, 0, false>;
+        else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1, false>;
+        else if (L && !C) kern = gx_fill_kernel<K, true, false, 2, false>;
+        else kern = gx_fill_kernel<K, true, true, 2, false>;
+    }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
@@ -194,7 +205,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
+    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -384,7 +395,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
     // ---- wavefront geometry
     pl->K = 8;
     const int K = pl->K, W = 32 * K;
-    const int GROUPS = 32 / (64 / K);
+    const uint32_t BATCH = (uint32_t)Geo<8>::BATCH, CPB = (uint32_t)Geo<8>::CPB;
     pl->pairs.resize(n_pairs);
     std::vector<TileDesc> tiles;
     std::vector<uint64_t> keys;
@@ -405,7 +416,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
         pd.progress_off = (uint32_t)progress;
         pd.tile_base = (uint32_t)best;
         const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
-        pd.tile_code_bytes = interior ? tile_blocks(rows_max) * GROUPS * 32 * 16 : 0;
+        pd.tile_code_bytes = interior ? tile_batches(rows_max, BATCH) * CPB * 32 * 16 : 0;
         if (interior) {
             colbuf += (uint64_t)(pd.S - 1) * m;
             top += n;
@@ -493,6 +504,34 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
             pl->h2d_bytes += pl->n_pairs * 16;
         }
     } else {
+        // alphabet of the batch: with <= 4 distinct bytes the fill uses the shared-memory profile path
+        bool seen[256] = {false};
+        int nsym = 0;
+        uint8_t lut[256];
+        memset(lut, 255, sizeof lut);
+        for (uint64_t q = 0; q < pl->n_pairs && nsym <= 4; ++q) {
+            const uint8_t *a = blob + off1[q], *b = blob + off2[q];
+            for (uint64_t k = 0; k < pl->len1[q]; ++k)
+                if (!seen[a[k]]) { seen[a[k]] = true; if (nsym < 4) lut[a[k]] = (uint8_t)nsym; nsym++; }
+            for (uint64_t k = 0; k < pl->len2[q]; ++k)
+                if (!seen[b[k]]) { seen[b[k]] = true; if (nsym < 4) lut[b[k]] = (uint8_t)nsym; nsym++; }
+        }
+        pl->prof = nsym <= 4 && pl->n_tiles > 0;
+        if (pl->prof) {
+            if (!pl->d_lut) {
+                int rc = pool_alloc(c, 256, (void **)&pl->d_lut);
+                if (rc) return rc;
+            }
+            pool_free(c, pl->d_blob_sym);
+            pl->d_blob_sym = nullptr;
+            int rc = pool_alloc(c, blob_len + 64, (void **)&pl->d_blob_sym);
+            if (rc) return rc;
+            pl->dev_bytes += blob_len + 64;
+            CK(cudaMemcpyAsync(pl->d_lut, lut, 256, cudaMemcpyHostToDevice, c->stream));
+            const int grid = (int)std::min<uint64_t>((blob_len + 64 + 255) / 256, (uint64_t)c->sm_count * 8);
+            gx_encode_kernel<<<grid, 256, 0, c->stream>>>(pl->d_blob, pl->d_blob_sym, (size_t)blob_len + 64, pl->d_lut);
+            CK(cudaGetLastError());
+        }
         for (uint64_t q = 0; q < pl->n_pairs; ++q) {
             pl->pairs[q].s1_off = off1[q];
             pl->pairs[q].s2_off = off2[q];
@@ -556,6 +595,8 @@ int gx_plan_execute(gx_plan *pl) {
     CK(cudaMemsetAsync(pl->d_ctrl, 0, (16 + pl->progress_entries) * 4, c->stream));
     FillParams fp;
     fp.blob = pl->d_blob;
+    fp.blob_sym = pl->prof ? pl->d_blob_sym : nullptr;
+    fp.one = 1u;
     fp.pairs = pl->d_pairs;
     fp.tiles = pl->d_tiles;
     fp.n_tiles = (uint32_t)pl->n_tiles;

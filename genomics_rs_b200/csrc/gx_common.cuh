@@ -17,7 +17,8 @@ constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
 // the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.
 constexpr int WARP_SMEM_S1 = PANEL_H + 32;
-constexpr int WARP_SMEM = WARP_SMEM_S1 + 256 + 256 + 16;
+constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 256 + 256 + 16;   // match/mismatch profile: 4 symbols x 256 columns x 4 B
+constexpr int WARP_SMEM = WARP_SMEM_PROF + 4096;
 
 struct PairDesc {
     uint64_t s1_off, s2_off;   // byte offsets of the two sequences in the device blob
@@ -46,6 +47,8 @@ struct DevResult {
 
 struct FillParams {
     const uint8_t *blob;
+    const uint8_t *blob_sym;         // blob re-encoded to symbols 0..3 (profile path), else null
+    uint32_t one;                    // the constant 1, opaque to ptxas (keeps code-bit IMADs on the FMA pipe)
     const PairDesc *pairs;
     const TileDesc *tiles;
     uint32_t n_tiles;

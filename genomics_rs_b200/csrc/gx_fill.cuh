@@ -13,17 +13,25 @@
 //           (E,I) that lane l-1 produced one step earlier -> two __shfl_up per step.
 //   strip -> strip hand-off (right boundary column, 8 B per row) goes through an L2-resident
 //           buffer with an LL-style protocol: one 64-bit store carries E, I and a parity bit of
-//           the current execute, the consumer polls the data itself, no flag, no fence.
+//           the current execute, the consumer polls the data itself, no flag, no fence.  Rows are
+//           published and consumed in batches of 8 so that a strip trails its left neighbour by
+//           ~50 steps only (pipeline ramp of a pair = strips x lag).
 //   panel -> panel hand-off (bottom row of a tile, (E,D) per column) goes through `top` with a
 //           release/acquire counter per strip (once per 4096 rows).
 //   tiles are taken from a global ticket counter in an order in which every dependency has a
 //   smaller ticket, so a waiting warp only ever waits for a warp that is already resident.
 //   s1 (the row sequence) is staged per tile into shared memory by a 1-D TMA bulk copy
-//   (cp.async.bulk + mbarrier); s2 characters of the lane's K columns live in registers.
+//   (cp.async.bulk + mbarrier); s2 enters either as K characters in registers (compare path) or,
+//   when the batch uses at most 4 distinct symbols, as a per-warp match/mismatch profile in shared
+//   memory (PROF): two conflict-free LDS.128 per row replace 2 ALU instructions per cell.
 //
-// Integer work per cell (global, score only): 2x VIADDMNMX (I, D), ISETP+SEL (match/mismatch),
-// IADD (S), VIMNMX3 (V), IADD (E) = 7 -- the figure bench.py's roofline uses.
+// Pipe budget per cell (PROF, what the SASS shows):
+//   score only   ALU: VIADDMNMX (I), VIADDMNMX (D), VIMNMX3 (V)      FMA pipe: IMAD.IADD (S), IMAD.IADD (E)
+//   with codes   + ALU: 2x ISETP                                      + FMA pipe: 2x predicated IMAD (code bits)
+// The contractual roofline of bench.py counts 7 / 8 / 13 INT32 ops per cell.
 #pragma once
+#include <type_traits>
+
 #include "gx_common.cuh"
 
 namespace gx {
@@ -31,7 +39,7 @@ namespace gx {
 constexpr unsigned FULL = 0xffffffffu;
 // A dependency wait that lasts longer than this many polls (>= ~1 s) is a bug or a lost device: raise the
 // abort word instead of hanging the GPU; every waiter also leaves as soon as it sees the word set.
-constexpr uint32_t SPIN_LIMIT = 1u << 23;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 __device__ __forceinline__ bool spin_check(uint32_t &spins, uint32_t *abort_word) {
     if (++spins > SPIN_LIMIT) atomicExch(abort_word, 1u);
@@ -41,25 +49,58 @@ __device__ __forceinline__ bool spin_check(uint32_t &spins, uint32_t *abort_word
     return false;
 }
 
-template <int K, bool LOCAL, bool CODES, int TRACK, bool MASKED, bool PAD>
-__device__ __forceinline__ void run_block(int (&eu)[K], int (&du)[K], const int (&c2)[K], int &elast, int &ilast, int &vd,
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
+
+// code bits of one cell added to a 32-bit code word: += UNIT if S != V, += UNIT again if also I != V.
+// Two ISETP on the ALU pipe, two predicated IMAD on the FMA pipe (`one` is an opaque register holding 1,
+// so ptxas cannot turn the IMADs back into ALU-pipe adds).
+template <uint32_t UNIT>
+__device__ __forceinline__ void code_acc(uint32_t &cw, int S, int I, int V, uint32_t one) {
+    asm("{\n\t.reg .pred p1, p2;\n\t"
+        "setp.ne.s32 p1, %1, %3;\n\t"
+        "setp.ne.and.s32 p2, %2, %3, p1;\n\t"
+        "@p1 mad.lo.u32 %0, %4, %5, %0;\n\t"
+        "@p2 mad.lo.u32 %0, %4, %5, %0;\n\t}"
+        : "+r"(cw)
+        : "r"(S), "r"(I), "r"(V), "r"(one), "n"(UNIT));
+}
+
+// geometry shared by fill, walk and host: steps are processed in batches of BATCH steps
+template <int K>
+struct Geo {
+    static constexpr int W = 32 * K;                       // columns per strip
+    static constexpr int SPC = 64 / K;                     // steps per 16-byte code chunk
+    static constexpr int BATCH = (SPC > 8) ? SPC : 8;      // steps per batch (boundary hand-off granularity)
+    static constexpr int CPB = BATCH / SPC;                // code chunks per batch
+    static constexpr int KB = Log2<K>::value;
+};
+__host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_t batch) { return (rows + 31 + batch - 1) / batch; }
+
+// One batch of BATCH systolic steps of one warp.
+template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD>
+__device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int &elast, int &ilast, int &vd,
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
-                                          const uint8_t *s1base /* s1 row 0 of this tile */, const uint2 *inring,
-                                          uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
+                                          const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
+                                          const uint8_t *prof_lane /* profile base + lane*16 */,
+                                          const uint2 *inr /* in-ring slot of step 0 of this batch */, uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
                                           const int kvalid) {
-    constexpr int SPC = 64 / K;       // steps per 16-byte code chunk
-    constexpr int GROUPS = 32 / SPC;
-    constexpr int KB = Log2<K>::value;
-#pragma unroll 1
-    for (int grp = 0; grp < GROUPS; ++grp) {
-        uint32_t cw[4] = {0u, 0u, 0u, 0u};
-        const uint2 *inr = inring + grp * SPC;
-        const int tg = t0 + grp * SPC;
-        const uint8_t *s1p = s1base + (tg - lane);
+    using G = Geo<K>;
+    constexpr int KB = G::KB;
+    const uint8_t *s1p = s1base + (t0 - lane);
 #pragma unroll
-        for (int uu = 0; uu < SPC; ++uu) {
-            const int r = tg + uu - lane;
-            const uint2 bnd = inr[uu];
+    for (int ch = 0; ch < G::CPB; ++ch) {
+        uint32_t cw[4] = {0u, 0u, 0u, 0u};
+        static_for<G::SPC>([&](auto uc) {
+            constexpr int uu = decltype(uc)::value;
+            const int step = ch * G::SPC + uu;          // step inside the batch (compile-time after unrolling)
+            const int r = t0 + step - lane;
+            const uint2 bnd = inr[step];
             int el = __shfl_up_sync(FULL, elast, 1);
             int il = __shfl_up_sync(FULL, ilast, 1);
             if (lane == 0) {
@@ -73,22 +114,35 @@ __device__ __forceinline__ void run_block(int (&eu)[K], int (&du)[K], const int 
                 const int rc = min(max(r, 0), rows - 1);
                 c1 = s1base[rc];
             } else {
-                c1 = s1p[uu];
+                c1 = s1p[step];
+            }
+            int sub[K];
+            if (PROF) {
+                // profile row of this row's symbol: [sym][k/4][lane][k%4] ints -> two conflict-free LDS.128
+                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + (c1 << 10));
+#pragma unroll
+                for (int q = 0; q < K / 4; ++q) {
+                    const int4 v = pp[q * 32];
+                    sub[4 * q + 0] = v.x;
+                    sub[4 * q + 1] = v.y;
+                    sub[4 * q + 2] = v.z;
+                    sub[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) sub[k] = (c1 == c2[k]) ? ap : bp;
             }
             int e = el, irun = il, ed = vd;
             int rowbest = -1;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
+            static_for<K>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
                 const int In = LOCAL ? __viaddmax_s32_relu(irun, g, e) : __viaddmax_s32(irun, g, e);
                 const int Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                const int Sn = ed + ((c1 == c2[k]) ? ap : bp);
+                const int Sn = ed + sub[k];
                 const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
                 if (CODES) {
-                    const uint32_t code = (Sn == Vn) ? 0u : ((In == Vn) ? 1u : 2u);
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int bitpos = uu * 2 * K + 2 * k;
-                    cw[bitpos >> 5] |= code << (bitpos & 31);
+                    constexpr int bitpos = uu * 2 * K + 2 * k;
+                    code_acc<(1u << (bitpos & 31))>(cw[bitpos >> 5], Sn, In, Vn, one);
                 }
                 ed = eu[k];
                 const int En = Vn + hg;
@@ -110,7 +164,7 @@ __device__ __forceinline__ void run_block(int (&eu)[K], int (&du)[K], const int 
                     if (PAD) key = (k < kvalid) ? key : -1;
                     rowbest = max(rowbest, key);
                 }
-            }
+            });
             if (MASKED) vd = active ? el : vd;
             else vd = el;
             elast = e;
@@ -125,20 +179,17 @@ __device__ __forceinline__ void run_block(int (&eu)[K], int (&du)[K], const int 
                 best = active ? max(best, rowbest) : best;
             }
             if (lane == 31 && active) outring[r & 31] = make_uint2((uint32_t)e, (uint32_t)irun);
-        }
-        if (CODES) st_cs_uint4(code_dst + grp * 32, make_uint4(cw[0], cw[1], cw[2], cw[3]));
+        });
+        if (CODES) st_cs_uint4(code_dst + ch * 32, make_uint4(cw[0], cw[1], cw[2], cw[3]));
     }
 }
 
-// steps of one tile with `rows` rows: rows + 31, rounded up to whole 32-step blocks
-__host__ __device__ __forceinline__ uint32_t tile_blocks(uint32_t rows) { return (rows + 31 + 31) / 32; }
-
-template <int K, bool LOCAL, bool CODES, int TRACK>
+template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF>
 __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(const FillParams P) {
-    constexpr int W = 32 * K;
-    constexpr int SPC = 64 / K;
-    constexpr int GROUPS = 32 / SPC;
-    constexpr int KB = Log2<K>::value;
+    using G = Geo<K>;
+    constexpr int W = G::W;
+    constexpr int B = G::BATCH;
+    constexpr int KB = G::KB;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -147,6 +198,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
     uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);
     uint2 *outring = inring + 32;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 32);
+    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints (K == 8: 4 KB)
 
     if (lane == 0) {
         mbar_init(mbar, 1);
@@ -155,9 +207,11 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
     __syncwarp();
     uint32_t phase = 0;
     const int g = P.g, hg = P.hg, ap = P.ap, bp = P.bp, h = P.h;
+    const uint32_t one = P.one;
     const uint32_t parity = P.parity;
     uint32_t *abort_word = P.ticket + 1;
     bool dead = false;
+    const uint8_t *seq = PROF ? P.blob_sym : P.blob;   // PROF: sequences re-encoded to symbols 0..3 (gx_encode_kernel)
 
     for (;;) {
         uint32_t tk = 0;
@@ -175,7 +229,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
         const bool has_pad = (s + 1) * W > n;
 
         // ---- stage s1[i0 .. i0+rows) with a TMA bulk copy (16-byte aligned window around it)
-        const uint8_t *s1g = P.blob + pd->s1_off + i0;
+        const uint8_t *s1g = seq + pd->s1_off + i0;
         const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(s1g) & 15u);
         __syncwarp();
         if (lane == 0) {
@@ -185,12 +239,25 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             tma_bulk_g2s(s1buf, s1g - delta, bytes, mbar);
         }
 
-        // ---- s2 characters of this lane's columns; padding columns never match (256)
+        // ---- s2 of this lane's columns: characters in registers, or the match/mismatch profile in smem
         int c2[K];
         {
-            const uint8_t *s2g = P.blob + pd->s2_off + jl;
+            const uint8_t *s2g = seq + pd->s2_off + jl;
 #pragma unroll
             for (int k = 0; k < K; ++k) c2[k] = (k < kvalid) ? (int)__ldg(s2g + k) : 256;
+        }
+        if (PROF) {
+#pragma unroll
+            for (int sym = 0; sym < 4; ++sym)
+#pragma unroll
+                for (int q = 0; q < K / 4; ++q) {
+                    int4 v;
+                    v.x = (c2[4 * q + 0] == sym) ? ap : bp;
+                    v.y = (c2[4 * q + 1] == sym) ? ap : bp;
+                    v.z = (c2[4 * q + 2] == sym) ? ap : bp;
+                    v.w = (c2[4 * q + 3] == sym) ? ap : bp;
+                    *reinterpret_cast<int4 *>(prof + (sym << 10) + q * 512 + lane * 16) = v;
+                }
         }
 
         // ---- top boundary of the tile: (E,D) of row i0 for this lane's columns
@@ -210,7 +277,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
                     dead = true;
                     break;
                 }
-                __nanosleep(200);
+                __nanosleep(400);
             }
             if (dead) break;
             const int2 *tp = P.top + pd->top_off + jl;
@@ -250,16 +317,16 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
 
         int elast = 0, ilast = 0;
         int best = -1, best_r = 0;
-        const uint32_t nblk = tile_blocks((uint32_t)rows);
+        const uint32_t nbat = tile_batches((uint32_t)rows, B);
         uint4 *code_base = nullptr;
         if (CODES)
             code_base = reinterpret_cast<uint4 *>(P.codes + pd->codes_off + (uint64_t)(p * S + s) * pd->tile_code_bytes) + lane;
 
-        // ---- left boundary prefetch (LL protocol): entry of local row 32*b + lane
+        // ---- left boundary prefetch (LL protocol): lanes 0..B-1 fetch the entries of local rows B*bt + lane
         unsigned long long nxt = 0;
-        auto issue = [&](uint32_t b) {
-            const int r = (int)(32u * b) + lane;
-            if (s > 0 && r < rows) nxt = ld_relaxed_u64(cb_in + r);
+        auto issue = [&](uint32_t bt) {
+            const int r = (int)(B * bt) + lane;
+            if (s > 0 && lane < B && r < rows) nxt = ld_relaxed_u64(cb_in + r);
         };
         issue(0);
 
@@ -278,58 +345,65 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
         }
         phase ^= 1u;
         const uint8_t *s1base = s1buf + delta;
+        const uint8_t *prof_lane = prof + lane * 16;
+        __syncwarp();   // profile stores visible to the whole warp
 
-        for (uint32_t b = 0; b < nblk; ++b) {
-            // settle the in-ring of this block
-            uint2 cur;
-            const int rb = (int)(32u * b) + lane;
-            if (s == 0) {
-                cur.x = (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
-                cur.y = (uint32_t)NEG32;
-            } else {
-                const bool need = rb < rows;
-                uint32_t spins = 0;
-                for (;;) {
-                    const bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
-                    if (__all_sync(FULL, ok)) break;
-                    if (__any_sync(FULL, spin_check(spins, abort_word))) {
-                        dead = true;
-                        break;
+        for (uint32_t bt = 0; bt < nbat; ++bt) {
+            const int t0 = (int)(B * bt);
+            // settle the B in-ring entries of this batch (rows t0 .. t0+B-1 of the left neighbour's last column)
+            {
+                uint2 cur;
+                const int rb = t0 + lane;
+                if (s == 0) {
+                    cur.x = (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
+                    cur.y = (uint32_t)NEG32;
+                } else {
+                    const bool need = (lane < B) && (rb < rows);
+                    uint32_t spins = 0;
+                    for (;;) {
+                        const bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
+                        if (__all_sync(FULL, ok)) break;
+                        if (__any_sync(FULL, spin_check(spins, abort_word))) {
+                            dead = true;
+                            break;
+                        }
+                        if (!ok) {
+                            __nanosleep(100);
+                            nxt = ld_relaxed_u64(cb_in + rb);
+                        }
                     }
-                    if (!ok) {
-                        __nanosleep(64);
-                        nxt = ld_relaxed_u64(cb_in + rb);
-                    }
+                    if (dead) break;
+                    cur.x = (uint32_t)nxt;
+                    cur.y = (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1);
                 }
-                if (dead) break;
-                cur.x = (uint32_t)nxt;
-                cur.y = (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1);
+                if (bt + 1 < nbat) issue(bt + 1);
+                if (lane < B) inring[(t0 + lane) & 31] = cur;
+                __syncwarp();
             }
-            if (b + 1 < nblk) issue(b + 1);
-            inring[lane] = cur;
-            __syncwarp();
 
-            const int t0 = (int)(32u * b);
-            const bool full = (b >= 1) && (t0 + 31 <= rows - 1);
-            uint4 *cdst = CODES ? code_base + (size_t)b * GROUPS * 32 : nullptr;
+            const bool full = (t0 >= 31) && (t0 + B - 1 <= rows - 1);
+            uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
             if (full) {
                 if ((TRACK != 0) && has_pad)
-                    run_block<K, LOCAL, CODES, TRACK, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp, s1base,
-                                                                   inring, outring, cdst, t0, rows, lane, kvalid);
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                         one, s1base, prof_lane, inring + (t0 & 31), outring, cdst, t0,
+                                                                         rows, lane, kvalid);
                 else
-                    run_block<K, LOCAL, CODES, TRACK, false, false>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                    s1base, inring, outring, cdst, t0, rows, lane, kvalid);
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, false>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap,
+                                                                          bp, one, s1base, prof_lane, inring + (t0 & 31), outring,
+                                                                          cdst, t0, rows, lane, kvalid);
             } else {
-                run_block<K, LOCAL, CODES, TRACK, true, (TRACK != 0)>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp, s1base,
-                                                                      inring, outring, cdst, t0, rows, lane, kvalid);
+                run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0)>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                            one, s1base, prof_lane, inring + (t0 & 31), outring, cdst,
+                                                                            t0, rows, lane, kvalid);
             }
 
-            // flush the right boundary rows lane 31 finished in this block: rows 32(b-1)+1 .. 32b
+            // publish the right-boundary rows lane 31 finished in this batch: rows t0-31 .. t0+B-32
             __syncwarp();
-            if (cb_out != nullptr) {
-                const int ro = (lane == 0) ? t0 : t0 - 32 + lane;
+            if (cb_out != nullptr && lane < B) {
+                const int ro = t0 - 31 + lane;
                 if (ro >= 0 && ro < rows) {
-                    const uint2 v = outring[lane];
+                    const uint2 v = outring[ro & 31];
                     const unsigned long long packed =
                         (unsigned long long)v.x | ((unsigned long long)((v.y << 1) | parity) << 32);
                     st_relaxed_u64(cb_out + ro, packed);
@@ -337,8 +411,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             }
             __syncwarp();
         }
-
         if (dead) break;
+
         // ---- bottom row -> top buffer (next panel of this strip, and the global score)
         {
             int2 *tp = P.top + pd->top_off + jl;
@@ -374,6 +448,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             if (lane == 0) P.tile_best[pd->tile_base + p * S + s] = make_int4(bv, bi, bj, 0);
         }
     }
+}
+
+// Re-encodes sequence bytes to dense symbols through a 256-entry table (PROF path): sym 0..3, 255 = not in alphabet.
+__global__ void __launch_bounds__(256) gx_encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
+                                                        const uint8_t *__restrict__ lut256) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = lut256[threadIdx.x];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = lut[in[i]];
 }
 
 }  // namespace gx

@@ -7,34 +7,17 @@
 //               off-by-one match label is_match(i,j) (algo.rs:354, sequence.rs:102-115),
 //               open/extend labels from last_choice (algo.rs:373-379,388-394),
 //               checked_sub index update (algo.rs:412-417), stop at (0,0) (algo.rs:419-421).
-// One warp per pair.  All 32 lanes replay the same scalar walk (uniform loads, no divergence);
-// the lanes are used to (a) prefetch the code lines a diagonal run will touch next and
-// (b) buffer 32 op bytes so that the ops list is written with coalesced 32-byte stores.
+// One warp per pair, two levels of parallelism inside the inherently sequential walk:
+// (a) a 128-row x 64-column window of code chunks around the current cell is fetched into shared memory with
+//     one round of independent 16-byte loads -- one HBM latency per window instead of one per code line;
+// (b) run following: the path consists of runs of equal codes, so lane x inspects the cell x moves ahead in
+//     the current direction, a ballot finds the run length, and up to 32 ops (labels, counters, coalesced
+//     byte stores) are emitted per iteration.
 #pragma once
 #include "gx_common.cuh"
+#include "gx_fill.cuh"
 
 namespace gx {
-
-template <int K>
-__device__ __forceinline__ const uint32_t *code_word_addr(const uint8_t *codes, const PairDesc *pd, uint32_t i, uint32_t j,
-                                                          uint32_t &shift) {
-    constexpr int W = 32 * K;
-    constexpr int SPC = 64 / K;
-    const uint32_t jj = j - 1, ii = i - 1;
-    const uint32_t s = jj / W;
-    const uint32_t l = (jj % W) / K;
-    const uint32_t k = jj % K;
-    const uint32_t p = ii >> PANEL_H_LOG2;
-    const uint32_t r = ii & (PANEL_H - 1);
-    const uint32_t t = r + l;
-    const uint32_t chunk = t / SPC;
-    const uint32_t u = t % SPC;
-    const uint32_t bitpos = u * 2 * K + 2 * k;
-    shift = bitpos & 31u;
-    const uint64_t off = pd->codes_off + (uint64_t)(p * pd->S + s) * pd->tile_code_bytes + ((uint64_t)chunk * 32u + l) * 16u +
-                         (bitpos >> 5) * 4u;
-    return reinterpret_cast<const uint32_t *>(codes + off);
-}
 
 template <int K>
 __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
@@ -101,63 +84,102 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     res.fill_ms = res.walk_ms = 0.0;
 
     if (P.traceback) {
+        using G = Geo<K>;
+        constexpr int SPC = G::SPC;
+        constexpr int WL = 8;                       // lanes (of the fill warp) per window  -> WL*K columns
+        constexpr int WR = 128;                     // rows per window
+        constexpr int NCH = (WR + WL + SPC - 1) / SPC + 2;   // code chunks per window lane
+        __shared__ uint4 win[WL * NCH];
         uint8_t *ops = P.ops + pd->ops_off;
         uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
         uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
-        uint32_t myop = 0;
-        for (;;) {
-            uint32_t c;
-            if (i == 0 && j == 0) c = 0;               // origin: sub_score == max == 0
-            else if (j == 0) c = local ? 3u : 2u;      // column 0: only delete_score is finite (global); local stops
-            else if (i == 0) c = local ? 3u : 1u;      // row 0
-            else {
-                uint32_t sh;
-                const uint32_t *wp = code_word_addr<K>(P.codes, pd, i, j, sh);
-                c = (__ldg(wp) >> sh) & 3u;
-                if ((nops & 7u) == 0u) {
-                    // prefetch along the diagonal: lane l touches the line of cell (i-8(l+1), j-8(l+1))
-                    const uint32_t d = 8u * (uint32_t)(lane + 1);
-                    if (i > d && j > d) {
-                        uint32_t sh2;
-                        const uint32_t *pp = code_word_addr<K>(P.codes, pd, i - d, j - d, sh2);
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+        // current window: tile (wp, ws), fill-lanes [wl0, wl1], local rows [wr0, wr1], first chunk wc0
+        uint32_t wp = 0xffffffffu, ws = 0, wl0 = 0, wl1 = 0, wr0 = 0, wr1 = 0, wc0 = 0;
+
+        // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (run must end before it)
+        auto cell_code = [&](uint32_t ci, uint32_t cj) -> uint32_t {
+            if (ci == 0 && cj == 0) return 0u;            // origin: sub_score == max == 0 (algo.rs:195-202)
+            if (cj == 0) return local ? 3u : 2u;          // column 0: only delete_score is finite; local stops
+            if (ci == 0) return local ? 3u : 1u;          // row 0
+            const uint32_t jj = cj - 1, ii = ci - 1;
+            const uint32_t s = jj / G::W, l = (jj % G::W) / K, k = jj % K;
+            const uint32_t p = ii >> PANEL_H_LOG2, r = ii & (PANEL_H - 1);
+            if (!(p == wp && s == ws && l >= wl0 && l <= wl1 && r >= wr0 && r <= wr1)) return 7u;
+            const uint32_t t = r + l;
+            const uint32_t bitpos = (t % SPC) * 2 * K + 2 * k;
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win + (l - wl0) * NCH + (t / SPC - wc0));
+            return (w32[bitpos >> 5] >> (bitpos & 31u)) & 3u;
+        };
+
+        if (i == 0 && j == 0) {
+            // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
+            if (lane == 0) ops[0] = 0;
+            nops = 1;
+            n_match = 1;
+        } else {
+            for (;;) {
+                uint32_t c0 = cell_code(i, j);
+                if (c0 == 7u) {
+                    // (re)load the window that ends at this cell: lanes [l-7, l] x rows [r-127, r] of its tile
+                    const uint32_t jj = j - 1, ii = i - 1;
+                    const uint32_t s = jj / G::W, l = (jj % G::W) / K;
+                    const uint32_t p = ii >> PANEL_H_LOG2, r = ii & (PANEL_H - 1);
+                    wp = p; ws = s;
+                    wl1 = l; wl0 = (l >= WL - 1) ? l - (WL - 1) : 0;
+                    wr1 = r; wr0 = (r >= WR - 1) ? r - (WR - 1) : 0;
+                    wc0 = (wr0 + wl0) / SPC;
+                    const uint32_t cmax = (wr1 + wl1) / SPC;
+                    const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
+                                                                         (uint64_t)(p * pd->S + s) * pd->tile_code_bytes);
+                    __syncwarp();
+                    for (uint32_t x = lane; x < WL * NCH; x += 32) {
+                        const uint32_t a = x / NCH, b = x % NCH;
+                        const uint32_t ch = wc0 + b, fl = wl0 + a;
+                        if (fl <= wl1 && ch <= cmax) win[x] = __ldcs(tile + (size_t)ch * 32 + fl);
                     }
+                    __syncwarp();
+                    c0 = cell_code(i, j);
                 }
+                if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
+                // every lane looks x steps ahead in the direction of c0; the run ends at the first different code
+                const uint32_t x = (uint32_t)lane;
+                const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
+                const bool reach = (x * di <= i) && (x * dj <= j);
+                const uint32_t ci = i - (reach ? x * di : 0u), cj = j - (reach ? x * dj : 0u);
+                uint32_t cx = reach ? cell_code(ci, cj) : 7u;
+                if (x > 0 && ci == 0 && cj == 0) cx = 7u;  // (0,0) is never emitted after a move (algo.rs:419-421)
+                const uint32_t same = __ballot_sync(0xffffffffu, cx == c0);
+                const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
+                const bool mine = x < run;
+                uint32_t op;
+                if (c0 == 0u) {
+                    const int a = (ci < m) ? (int)__ldg(s1 + ci) : -1;   // is_match(i, j): Option<u8>, None == None
+                    const int b = (cj < n) ? (int)__ldg(s2 + cj) : -1;
+                    op = (a == b) ? 0u : 1u;
+                    const uint32_t mm = __ballot_sync(0xffffffffu, mine && op == 0u);
+                    n_match += (uint32_t)__popc(mm);
+                    n_mis += run - (uint32_t)__popc(mm);
+                    last = 0u;
+                } else {
+                    const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
+                    const bool opens = (last != ext);                  // algo.rs:373-379, 388-394
+                    op = (x == 0 && opens) ? ext + 2u : ext;           // OpenInsert = 4, OpenDelete = 5
+                    n_open += opens ? 1u : 0u;
+                    n_ext += opens ? run - 1u : run;
+                    last = ext;
+                }
+                if (mine) ops[nops + x] = (uint8_t)op;
+                nops += run;
+                // last emitted cell, then the checked_sub move (algo.rs:412-417); run cells are all inside the table
+                res.end_i = i - (run - 1u) * di;
+                res.end_j = j - (run - 1u) * dj;
+                const bool i_none = di && (i < run), j_none = dj && (j < run);
+                if (i_none && j_none) break;
+                i = i_none ? 0u : i - run * di;
+                j = j_none ? 0u : j - run * dj;
+                if (i == 0 && j == 0) break;
             }
-            if (c == 3u) break;
-            uint32_t op;
-            bool i_none = false, j_none = false;
-            uint32_t ni = i, nj = j;
-            if (c == 0u) {
-                const int a = (i < m) ? (int)__ldg(s1 + i) : -1;   // Option<u8>: None == None is a match
-                const int b = (j < n) ? (int)__ldg(s2 + j) : -1;
-                if (a == b) { op = 0u; n_match++; }
-                else { op = 1u; n_mis++; }
-                last = op;
-                if (i == 0) i_none = true; else ni = i - 1;
-                if (j == 0) j_none = true; else nj = j - 1;
-            } else if (c == 1u) {
-                if (last == 2u) { op = 2u; n_ext++; }
-                else { op = 4u; n_open++; }
-                last = 2u;
-                if (j == 0) j_none = true; else nj = j - 1;
-            } else {
-                if (last == 3u) { op = 3u; n_ext++; }
-                else { op = 5u; n_open++; }
-                last = 3u;
-                if (i == 0) i_none = true; else ni = i - 1;
-            }
-            if ((nops & 31u) == (uint32_t)lane) myop = op;
-            res.end_i = i;
-            res.end_j = j;
-            nops++;
-            if ((nops & 31u) == 0u) ops[nops - 32u + lane] = (uint8_t)myop;
-            if (i_none && j_none) break;
-            i = i_none ? 0u : ni;
-            j = j_none ? 0u : nj;
-            if (i == 0 && j == 0) break;
         }
-        if ((uint32_t)lane < (nops & 31u)) ops[(nops & ~31u) + lane] = (uint8_t)myop;
         res.n_ops = nops;
         res.matches = n_match;
         res.mismatches = n_mis;

@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-constexpr int ITERS = 2048;
+constexpr int ITERS = 16384;
 #define CH 12
 
 template <int OP>
@@ -48,21 +48,38 @@ __global__ void __launch_bounds__(256) probe(int *sink, long long *cycles, int s
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+
+__global__ void calib(long long *out) {
+    // SM clock vs wall clock: one warp spins ~2 ms
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    const long long c0 = clock64();
+    long long c1 = c0;
+    while (c1 - c0 < 4000000) c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (threadIdx.x == 0) { out[0] = c1 - c0; out[1] = (long long)(g1 - g0); }
+}
+
+static double g_ghz = 0;
+
 template <int OP>
 void run(const char *name, int per_iter, int sms, int *sink, long long *cyc) {
-    for (int cps = 1; cps <= 4; cps *= 2) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int cps = 1; cps <= 8; cps *= 2) {
         const int grid = sms * cps;
         probe<OP><<<grid, 256>>>(sink, cyc, 11);
-        probe<OP><<<grid, 256>>>(sink, cyc, 13);
         cudaDeviceSynchronize();
-        long long *h = new long long[grid];
-        cudaMemcpy(h, cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-        double avg = 0;
-        for (int k = 0; k < grid; ++k) avg += (double)h[k];
-        avg /= grid;
-        delete[] h;
-        const double winstr = (double)ITERS * CH * per_iter * 8 * cps;
-        printf("%-34s warps/SM=%2d  %.3f warp-instr/clk/SM  (%.1f lanes/clk/SM)\n", name, 8 * cps, winstr / avg, 32 * winstr / avg);
+        cudaEventRecord(e0);
+        probe<OP><<<grid, 256>>>(sink, cyc, 13);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double cycles = ms * 1e-3 * g_ghz * 1e9;     // SM cycles of the whole launch
+        const double winstr = (double)ITERS * CH * per_iter * 8 * cps;   // per SM
+        printf("%-34s warps/SM=%2d  %.3f warp-instr/clk/SM  (%.1f lanes/clk/SM)  [%.3f ms]\n", name, 8 * cps, winstr / cycles,
+               32 * winstr / cycles, ms);
     }
 }
 
@@ -71,10 +88,15 @@ int main() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int *sink; long long *cyc;
     cudaMalloc(&sink, 64); cudaMalloc(&cyc, sizeof(long long) * sms * 8);
+    calib<<<1, 32>>>(cyc); calib<<<1, 32>>>(cyc);
+    cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    g_ghz = (double)h[0] / (double)h[1];
+    printf("SM clock from clock64/globaltimer: %.4f GHz; rates below use whole-launch CUDA-event time (launch overhead included)\n", g_ghz);
     run<0>("IADD imm", 1, sms, sink, cyc);
     run<1>("IADD 2-reg", 1, sms, sink, cyc);
     run<2>("LOP3 3-reg", 1, sms, sink, cyc);
-    run<3>("LOP3 imm", 1, sms, sink, cyc);
     run<4>("VIADDMNMX r,r,r", 1, sms, sink, cyc);
     run<5>("VIADDMNMX r,imm,r", 1, sms, sink, cyc);
     run<6>("VIMNMX3 r,r,r", 1, sms, sink, cyc);
