@@ -2,6 +2,7 @@
 // No CPU compute path exists in this file: every entry point needs a live sm_100 device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -17,7 +18,8 @@ namespace gx {
 
 static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
 static_assert(sizeof(PairDesc) == 80, "PairDesc layout");
-static_assert(WARP_SMEM % 16 == 0, "per-warp smem must keep 16 B alignment");
+static_assert(warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
+              "per-warp smem must keep 16 B alignment");
 
 // ------------------------------------------------------------------------------------------------
 struct Block {
@@ -126,6 +128,8 @@ struct gx_plan {
     uint8_t *d_blob = nullptr;
     uint8_t *d_blob_sym = nullptr;     // blob re-encoded to symbols 0..3 when the batch uses <= 4 distinct bytes
     uint8_t *d_lut = nullptr;
+    unsigned long long *d_stats = nullptr;   // GX_FILL_STATS=1: wait/tile cycle counters of the last execute
+    unsigned long long h_stats[8] = {0};
     bool prof = false;
     gx::PairDesc *d_pairs = nullptr;
     gx::TileDesc *d_tiles = nullptr;
@@ -153,7 +157,7 @@ namespace gx {
 template <int K>
 static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
     Ctx *c = pl->ctx;
-    const size_t smem = (size_t)WARPS_PER_CTA * WARP_SMEM;
+    const size_t smem = (size_t)WARPS_PER_CTA * warp_smem_bytes(K);
     void (*kern)(const FillParams) = nullptr;
     const bool L = pl->is_local != 0, C = pl->traceback;
     if (pl->prof) {
@@ -175,6 +179,7 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
     if (occ < 1) occ = 1;
     uint64_t want = (pl->n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     uint64_t cap = (uint64_t)c->sm_count * occ;
+    if (getenv("GX_GRID_CAP")) grid_cap = atoi(getenv("GX_GRID_CAP"));
     if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
     int grid = (int)std::min<uint64_t>(want, cap);
     if (grid < 1) grid = 1;
@@ -205,7 +210,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
+    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -392,10 +397,24 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
         return GX_OK;
     }
 
-    // ---- wavefront geometry
-    pl->K = 8;
+    // ---- wavefront geometry: K columns per lane.  Larger K amortises the per-step hand-off over more cells,
+    // smaller K gives more strips (warps) for batches that cannot fill the GPU otherwise.
+    {
+        const uint64_t resident = (uint64_t)c->sm_count * 2 * WARPS_PER_CTA;
+        uint64_t strips16 = 0, strips8 = 0;
+        for (uint64_t q = 0; q < n_pairs; ++q)
+            if (len1[q] && len2[q]) {
+                strips16 += (len2[q] + 511) / 512;
+                strips8 += (len2[q] + 255) / 256;
+            }
+        pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 2 >= resident || max_len < 2048) ? 8 : 4);
+        if (const char *e = getenv("GX_K")) {
+            const int k = atoi(e);
+            if (k == 4 || k == 8 || k == 16) pl->K = k;
+        }
+    }
     const int K = pl->K, W = 32 * K;
-    const uint32_t BATCH = (uint32_t)Geo<8>::BATCH, CPB = (uint32_t)Geo<8>::CPB;
+    const uint32_t SPC = 64u / (uint32_t)K, BATCH = SPC > 8 ? SPC : 8, CPB = BATCH / SPC;
     pl->pairs.resize(n_pairs);
     std::vector<TileDesc> tiles;
     std::vector<uint64_t> keys;
@@ -433,7 +452,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
         for (uint32_t p = 0; p < pd.P; ++p)
             for (uint32_t s = 0; s < pd.S; ++s) {
                 tiles.push_back({(uint32_t)q, p, s, 0});
-                keys.push_back(((uint64_t)p * PANEL_H + (uint64_t)s * 96) << 24 | (q & 0xffffff));
+                keys.push_back(((uint64_t)p * PANEL_H + (uint64_t)s * 64) << 24 | (q & 0xffffff));
             }
     }
     {
@@ -597,6 +616,16 @@ int gx_plan_execute(gx_plan *pl) {
     fp.blob = pl->d_blob;
     fp.blob_sym = pl->prof ? pl->d_blob_sym : nullptr;
     fp.one = 1u;
+    fp.stats = nullptr;
+    fp.start_lead = getenv("GX_START_LEAD") ? (uint32_t)atoi(getenv("GX_START_LEAD")) : 0u;
+    if (getenv("GX_FILL_STATS")) {
+        if (!pl->d_stats) {
+            int rc = pool_alloc(c, 64, (void **)&pl->d_stats);
+            if (rc) return rc;
+        }
+        CK(cudaMemsetAsync(pl->d_stats, 0, 64, c->stream));
+        fp.stats = pl->d_stats;
+    }
     fp.pairs = pl->d_pairs;
     fp.tiles = pl->d_tiles;
     fp.n_tiles = (uint32_t)pl->n_tiles;
@@ -613,7 +642,7 @@ int gx_plan_execute(gx_plan *pl) {
     fp.ap = sc.s_match - fp.hg;
     fp.bp = sc.s_mismatch - fp.hg;
     if (pl->n_tiles) {
-        int rc = launch_fill<8>(pl, fp, 0);
+        int rc = pl->K == 16 ? launch_fill<16>(pl, fp, 0) : pl->K == 4 ? launch_fill<4>(pl, fp, 0) : launch_fill<8>(pl, fp, 0);
         if (rc) return rc;
         pl->launches++;
     }
@@ -630,18 +659,19 @@ int gx_plan_execute(gx_plan *pl) {
     wp.g = sc.g;
     wp.h = sc.h;
     wp.hg = fp.hg;
-    wp.kcols_log2 = 3;
+    wp.kcols_log2 = pl->K == 16 ? 4 : pl->K == 4 ? 2 : 3;
     wp.is_local = pl->is_local;
     wp.traceback = pl->traceback ? 1 : 0;
     wp.have_best = pl->track == 2 ? 1 : 0;
     {
-        int rc = launch_walk<8>(pl, wp);
+        int rc = pl->K == 16 ? launch_walk<16>(pl, wp) : pl->K == 4 ? launch_walk<4>(pl, wp) : launch_walk<8>(pl, wp);
         if (rc) return rc;
         pl->launches++;
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
     uint32_t abort_word = 0;
     CK(cudaMemcpyAsync(&abort_word, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (fp.stats) CK(cudaMemcpyAsync(pl->h_stats, pl->d_stats, 64, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (abort_word) {
         g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";
@@ -740,6 +770,8 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 7: return (double)pl->d2h_bytes;
         case 8: return (double)pl->n_tiles;
         case 9: return (double)pl->kind;
+        case 15: return (double)pl->K;
+        case 10: case 11: case 12: case 13: case 14: return (double)pl->h_stats[what - 10];
         default: return -1.0;
     }
 }

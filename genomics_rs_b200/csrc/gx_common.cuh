@@ -17,8 +17,9 @@ constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
 // the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.
 constexpr int WARP_SMEM_S1 = PANEL_H + 32;
-constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 256 + 256 + 16;   // match/mismatch profile: 4 symbols x 256 columns x 4 B
-constexpr int WARP_SMEM = WARP_SMEM_PROF + 4096;
+constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 256 + 256 + 16;   // offset of the match/mismatch profile
+// profile: 4 symbols x (32*K columns) x 4 B = K*512 bytes per warp
+__host__ __device__ constexpr int warp_smem_bytes(int K) { return WARP_SMEM_PROF + K * 512; }
 
 struct PairDesc {
     uint64_t s1_off, s2_off;   // byte offsets of the two sequences in the device blob
@@ -59,6 +60,8 @@ struct FillParams {
     int2 *top;
     uint8_t *codes;
     int4 *tile_best;
+    uint32_t start_lead;             // rows of extra lead a strip waits for before its first batch (slack against convoys)
+    unsigned long long *stats;       // optional (null in production): [0] top-wait, [1] boundary-wait, [2] tile, [3] s1-wait cycles, [4] tiles
     int g, hg, ap, bp, h;            // ap = s_match - (h+g), bp = s_mismatch - (h+g): S is formed in E-space (E = V + h + g)
 };
 

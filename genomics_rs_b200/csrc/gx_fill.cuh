@@ -88,7 +88,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
                                           const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
                                           const uint8_t *prof_lane /* profile base + lane*16 */,
-                                          const uint2 *inr /* in-ring slot of step 0 of this batch */, uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
+                                          const uint2 *inr /* left-boundary (E,I) of this batch's steps */, uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
                                           const int kvalid) {
     using G = Geo<K>;
     constexpr int KB = G::KB;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
             int sub[K];
             if (PROF) {
                 // profile row of this row's symbol: [sym][k/4][lane][k%4] ints -> two conflict-free LDS.128
-                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + (c1 << 10));
+                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
 #pragma unroll
                 for (int q = 0; q < K / 4; ++q) {
                     const int4 v = pp[q * 32];
@@ -178,14 +178,14 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
             } else if (TRACK == 1) {
                 best = active ? max(best, rowbest) : best;
             }
-            if (lane == 31 && active) outring[r & 31] = make_uint2((uint32_t)e, (uint32_t)irun);
+            if (lane == 31 && active) outring[step] = make_uint2((uint32_t)e, (uint32_t)irun);   // row t0+step-31
         });
         if (CODES) st_cs_uint4(code_dst + ch * 32, make_uint4(cw[0], cw[1], cw[2], cw[3]));
     }
 }
 
 template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF>
-__global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(const FillParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParams P) {
     using G = Geo<K>;
     constexpr int W = G::W;
     constexpr int B = G::BATCH;
@@ -193,12 +193,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    uint8_t *wsm = smem + wib * WARP_SMEM;
+    uint8_t *wsm = smem + wib * warp_smem_bytes(K);
     uint8_t *s1buf = wsm;
     uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);
     uint2 *outring = inring + 32;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 32);
-    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints (K == 8: 4 KB)
+    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints = K*512 bytes
 
     if (lane == 0) {
         mbar_init(mbar, 1);
@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
         if (lane == 0) tk = atomicAdd(P.ticket, 1u);
         tk = __shfl_sync(FULL, tk, 0);
         if (tk >= P.n_tiles) break;
+        const long long st_t0 = P.stats ? clock64() : 0;
+        long long st_top = 0, st_bnd = 0, st_s1 = 0;
         const TileDesc td = P.tiles[tk];
         const PairDesc *pd = P.pairs + td.pair;
         const int m = (int)pd->m, n = (int)pd->n, S = (int)pd->S;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
                     v.y = (c2[4 * q + 1] == sym) ? ap : bp;
                     v.z = (c2[4 * q + 2] == sym) ? ap : bp;
                     v.w = (c2[4 * q + 3] == sym) ? ap : bp;
-                    *reinterpret_cast<int4 *>(prof + (sym << 10) + q * 512 + lane * 16) = v;
+                    *reinterpret_cast<int4 *>(prof + sym * (K * 128) + q * 512 + lane * 16) = v;
                 }
         }
 
@@ -272,13 +274,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             // the previous panel of this strip must be complete (its `top` rows written)
             const uint32_t *pr = P.progress + pd->progress_off + s;
             uint32_t spins = 0;
+            const long long w0 = P.stats ? clock64() : 0;
             while (ld_acquire_u32(pr) < (uint32_t)p) {
                 if (spin_check(spins, abort_word)) {
                     dead = true;
                     break;
                 }
-                __nanosleep(400);
+                __nanosleep(1000);
             }
+            if (P.stats) st_top += clock64() - w0;
             if (dead) break;
             const int2 *tp = P.top + pd->top_off + jl;
 #pragma unroll
@@ -328,11 +332,28 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             const int r = (int)(B * bt) + lane;
             if (s > 0 && lane < B && r < rows) nxt = ld_relaxed_u64(cb_in + r);
         };
+        if (s > 0 && P.start_lead > 0) {
+            // slack: do not start before the left neighbour is start_lead rows into this panel
+            const int lead = min((int)P.start_lead, rows - 1);
+            uint32_t spins = 0;
+            const long long w0 = P.stats ? clock64() : 0;
+            while ((((uint32_t)(ld_relaxed_u64(cb_in + lead) >> 32)) & 1u) != parity) {
+                if (spin_check(spins, abort_word)) {
+                    dead = true;
+                    break;
+                }
+                __nanosleep(500);
+            }
+            if (P.stats) st_bnd += clock64() - w0;
+            dead = __any_sync(FULL, dead);
+            if (dead) break;
+        }
         issue(0);
 
         // wait for the s1 segment
         {
             uint32_t tries = 0;
+            const long long w0 = P.stats ? clock64() : 0;
             while (!mbar_try_wait(mbar, phase)) {
                 if (++tries > (1u << 24)) {
                     atomicExch(abort_word, 1u);
@@ -341,6 +362,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
                 }
             }
             dead = __any_sync(FULL, dead);
+            if (P.stats) st_s1 += clock64() - w0;
             if (dead) break;
         }
         phase ^= 1u;
@@ -360,24 +382,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
                 } else {
                     const bool need = (lane < B) && (rb < rows);
                     uint32_t spins = 0;
+                    long long w0 = 0;
                     for (;;) {
                         const bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
                         if (__all_sync(FULL, ok)) break;
+                        if (P.stats && spins == 0) w0 = clock64();
                         if (__any_sync(FULL, spin_check(spins, abort_word))) {
                             dead = true;
                             break;
                         }
-                        if (!ok) {
-                            __nanosleep(100);
-                            nxt = ld_relaxed_u64(cb_in + rb);
-                        }
+                        // not there yet: fall back far enough that the next batches find their data ready
+                        __nanosleep(spins == 1 ? 1500 : 300);
+                        if (!ok) nxt = ld_relaxed_u64(cb_in + rb);
                     }
+                    if (P.stats && spins) st_bnd += clock64() - w0;
                     if (dead) break;
                     cur.x = (uint32_t)nxt;
                     cur.y = (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1);
                 }
                 if (bt + 1 < nbat) issue(bt + 1);
-                if (lane < B) inring[(t0 + lane) & 31] = cur;
+                if (lane < B) inring[lane] = cur;
                 __syncwarp();
             }
 
@@ -386,15 +410,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             if (full) {
                 if ((TRACK != 0) && has_pad)
                     run_batch<K, LOCAL, CODES, TRACK, PROF, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                         one, s1base, prof_lane, inring + (t0 & 31), outring, cdst, t0,
+                                                                         one, s1base, prof_lane, inring, outring, cdst, t0,
                                                                          rows, lane, kvalid);
                 else
                     run_batch<K, LOCAL, CODES, TRACK, PROF, false, false>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap,
-                                                                          bp, one, s1base, prof_lane, inring + (t0 & 31), outring,
+                                                                          bp, one, s1base, prof_lane, inring, outring,
                                                                           cdst, t0, rows, lane, kvalid);
             } else {
                 run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0)>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                            one, s1base, prof_lane, inring + (t0 & 31), outring, cdst,
+                                                                            one, s1base, prof_lane, inring, outring, cdst,
                                                                             t0, rows, lane, kvalid);
             }
 
@@ -403,13 +427,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
             if (cb_out != nullptr && lane < B) {
                 const int ro = t0 - 31 + lane;
                 if (ro >= 0 && ro < rows) {
-                    const uint2 v = outring[ro & 31];
+                    const uint2 v = outring[lane];
                     const unsigned long long packed =
                         (unsigned long long)v.x | ((unsigned long long)((v.y << 1) | parity) << 32);
                     st_relaxed_u64(cb_out + ro, packed);
                 }
             }
-            __syncwarp();
+            // (the __syncwarp of the next settle orders these out-ring reads before lane 31 writes again)
         }
         if (dead) break;
 
@@ -446,6 +470,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (K <= 8) ? 3 : 2) gx_fill_kernel(
                 bj = take ? oj : bj;
             }
             if (lane == 0) P.tile_best[pd->tile_base + p * S + s] = make_int4(bv, bi, bj, 0);
+        }
+        if (P.stats && lane == 0) {
+            atomicAdd(P.stats + 0, (unsigned long long)st_top);
+            atomicAdd(P.stats + 1, (unsigned long long)st_bnd);
+            atomicAdd(P.stats + 2, (unsigned long long)(clock64() - st_t0));
+            atomicAdd(P.stats + 3, (unsigned long long)st_s1);
+            atomicAdd(P.stats + 4, 1ull);
         }
     }
 }

@@ -106,11 +106,15 @@ def test_random_small_vs_faithful(gx, oracle, scores):
             _same(r, o, oracle, f"m={len(a)} n={len(b)} {scores} local={is_local}")
 
 
-def test_random_medium_ragged_vs_linear(gx, oracle):
-    """sizes that cross strip (256 columns), block (32 rows) and panel (4096 rows) boundaries"""
+@pytest.mark.parametrize("k", [4, 8, 16])
+def test_random_medium_ragged_vs_linear(gx, oracle, k, monkeypatch):
+    """sizes that cross strip (32*K columns), batch (8 rows) and panel (4096 rows) boundaries, for every
+    register-blocking factor K the library can pick (GX_K forces it)"""
+    monkeypatch.setenv("GX_K", str(k))
     rng = np.random.default_rng(11)
     dims = [(255, 256), (256, 257), (257, 255), (31, 600), (33, 1025), (1000, 31), (513, 513), (4095, 300), (4096, 300),
-            (4097, 300), (4200, 520), (300, 4200), (8193, 770), (1, 3000), (3000, 1)]
+            (4097, 300), (4200, 520), (300, 4200), (8193, 770), (1, 3000), (3000, 1), (127, 129), (129, 127), (511, 512),
+            (64, 1030)]
     pairs = [random_pair(rng, m, n, similar=(k % 3 != 0)) for k, (m, n) in enumerate(dims)]
     for is_local in (False, True):
         got = gx.align_batch(pairs, CONFIG_TOML, is_local)
@@ -130,6 +134,17 @@ def test_score_only_and_start_cell(gx, oracle):
         got = gx.align_batch(pairs, CONFIG_TOML, is_local, traceback=False)
         for (a, b), r in zip(pairs, got):
             assert r.score == oracle.score_linear(a, b, CONFIG_TOML, is_local)[0]
+
+
+@pytest.mark.parametrize("k", [4, 16])
+@pytest.mark.parametrize("is_local", [False, True])
+def test_brca2_other_blockings(gx, oracle, goldens, k, is_local, monkeypatch):
+    monkeypatch.setenv("GX_K", str(k))
+    g = next(p for p in goldens["pairs"] if p["fixture"] == "Human-Mouse-BRCA2-cds" and p["is_local"] == is_local)
+    s = read_fasta_gz("Human-Mouse-BRCA2-cds")
+    a = gx.align_batch([(s[0][1], s[1][1])], CONFIG_TOML, is_local)[0]
+    assert a.score == g["score"] and list(a.start) == g["start"] and list(a.end) == g["end"] and len(a.ops) == g["n_ops"]
+    assert "%016x" % oracle.hash_ops(a.ops, a.start) == g["op_hash"]
 
 
 def test_plan_reexecute_is_idempotent(gx, oracle):
