@@ -1,0 +1,53 @@
+//! ffi.rs -- NOT COMPILED IN THIS ENVIRONMENT.  `extern "C"` declarations of include/gxalign.h.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct gx_scores {
+    pub s_match: i32,
+    pub s_mismatch: i32,
+    pub g: i32,
+    pub h: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct gx_result {
+    pub score: i64,
+    pub start_i: u64,
+    pub start_j: u64,
+    pub end_i: u64,
+    pub end_j: u64,
+    pub n_ops: u64,
+    pub matches: u64,
+    pub mismatches: u64,
+    pub gap_extensions: u64,
+    pub opening_gaps: u64,
+    pub lcs_at_first_max: u64,
+    pub fill_ms: f64,
+    pub walk_ms: f64,
+}
+
+pub const GX_OK: c_int = 0;
+pub const GX_FLAG_TRACEBACK: c_int = 1;
+
+extern "C" {
+    pub fn gx_init(device: c_int) -> c_int;
+    pub fn gx_shutdown();
+    pub fn gx_strerror(status: c_int) -> *const c_char;
+    pub fn gx_last_error() -> *const c_char;
+    pub fn gx_align_pair(
+        s1: *const u8, m: u64, s2: *const u8, n: u64, sc: gx_scores, is_local: c_int, flags: c_int,
+        out: *mut gx_result, ops: *mut u8, ops_cap: u64,
+    ) -> c_int;
+    pub fn gx_align_batch(
+        seq_blob: *const u8, blob_len: u64, off1: *const u64, len1: *const u64, off2: *const u64, len2: *const u64,
+        n_pairs: u64, sc: gx_scores, is_local: c_int, flags: c_int, out: *mut gx_result, ops_blob: *mut u8,
+        ops_off: *const u64,
+    ) -> c_int;
+    pub fn gx_score_batch(
+        seq_blob: *const u8, blob_len: u64, off1: *const u64, len1: *const u64, off2: *const u64, len2: *const u64,
+        n_pairs: u64, sc: gx_scores, is_local: c_int, scores: *mut i64,
+    ) -> c_int;
+}
