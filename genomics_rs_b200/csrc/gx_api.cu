@@ -663,6 +663,7 @@ int gx_plan_execute(gx_plan *pl) {
     wp.is_local = pl->is_local;
     wp.traceback = pl->traceback ? 1 : 0;
     wp.have_best = pl->track == 2 ? 1 : 0;
+    wp.debug = getenv("GX_WALK_STATS") ? 1 : 0;
     {
         int rc = pl->K == 16 ? launch_walk<16>(pl, wp) : pl->K == 4 ? launch_walk<4>(pl, wp) : launch_walk<8>(pl, wp);
         if (rc) return rc;
@@ -718,8 +719,9 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
     }
     CK(cudaStreamSynchronize(c->stream));
     int rc = GX_OK;
+    const bool walk_dbg = getenv("GX_WALK_STATS") != nullptr;
     for (uint64_t q = 0; q < pl->n_pairs; ++q) {
-        out[q].fill_ms = pl->fill_ms;
+        if (!walk_dbg) out[q].fill_ms = pl->fill_ms;
         out[q].walk_ms = pl->walk_ms;
         if (pl->traceback) {
             const uint64_t cap = ops_off[q + 1] - ops_off[q];

@@ -77,6 +77,7 @@ struct WalkParams {
     int g, hg, h;
     int kcols_log2;                  // log2(K) of the fill kernel that wrote the codes
     int is_local, traceback, have_best;
+    int debug;                       // GX_WALK_STATS: iterations/reloads/cycles returned in spare result fields
 };
 
 // ---------------------------------------------------------------------------------------------

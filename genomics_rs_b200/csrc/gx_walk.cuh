@@ -8,8 +8,8 @@
 //               open/extend labels from last_choice (algo.rs:373-379,388-394),
 //               checked_sub index update (algo.rs:412-417), stop at (0,0) (algo.rs:419-421).
 // One warp per pair, two levels of parallelism inside the inherently sequential walk:
-// (a) a 128-row x 64-column window of code chunks around the current cell is fetched into shared memory with
-//     one round of independent 16-byte loads -- one HBM latency per window instead of one per code line;
+// (a) a 256-row window of code chunks spanning the whole strip is fetched into shared memory with one round
+//     of asynchronous 16-byte copies (cp.async) -- one HBM latency per window instead of one per code line;
 // (b) run following: the path consists of runs of equal codes, so lane x inspects the cell x moves ahead in
 //     the current direction, a ballot finds the run length, and up to 32 ops (labels, counters, coalesced
 //     byte stores) are emitted per iteration.
@@ -86,17 +86,16 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     if (P.traceback) {
         using G = Geo<K>;
         constexpr int SPC = G::SPC;
-        constexpr int WL = 8;                       // lanes (of the fill warp) per window  -> WL*K columns
-        constexpr int WR = 128;                     // rows per window
-        constexpr int NCH = (WR + WL + SPC - 1) / SPC + 2;   // code chunks per window lane
-        __shared__ uint4 win[WL * NCH];
+        constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
+        constexpr int NCH = (WR + 32 + SPC - 1) / SPC + 1;    // code chunks per fill-lane in a window
+        __shared__ uint4 win[NCH * 32];                       // [chunk][fill-lane]
         uint8_t *ops = P.ops + pd->ops_off;
         uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
         uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
-        // current window: tile (wp, ws), fill-lanes [wl0, wl1], local rows [wr0, wr1], first chunk wc0
-        uint32_t wp = 0xffffffffu, ws = 0, wl0 = 0, wl1 = 0, wr0 = 0, wr1 = 0, wc0 = 0;
+        // current window: tile (wp, ws), local rows [wr0, wr1], first chunk wc0
+        uint32_t wp = 0xffffffffu, ws = 0, wr0 = 0, wr1 = 0, wc0 = 0;
 
-        // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (run must end before it)
+        // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (a run must end before it)
         auto cell_code = [&](uint32_t ci, uint32_t cj) -> uint32_t {
             if (ci == 0 && cj == 0) return 0u;            // origin: sub_score == max == 0 (algo.rs:195-202)
             if (cj == 0) return local ? 3u : 2u;          // column 0: only delete_score is finite; local stops
@@ -104,13 +103,31 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             const uint32_t jj = cj - 1, ii = ci - 1;
             const uint32_t s = jj / G::W, l = (jj % G::W) / K, k = jj % K;
             const uint32_t p = ii >> PANEL_H_LOG2, r = ii & (PANEL_H - 1);
-            if (!(p == wp && s == ws && l >= wl0 && l <= wl1 && r >= wr0 && r <= wr1)) return 7u;
+            if (!(p == wp && s == ws && r >= wr0 && r <= wr1)) return 7u;
             const uint32_t t = r + l;
             const uint32_t bitpos = (t % SPC) * 2 * K + 2 * k;
-            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win + (l - wl0) * NCH + (t / SPC - wc0));
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win + (t / SPC - wc0) * 32 + l);
             return (w32[bitpos >> 5] >> (bitpos & 31u)) & 3u;
         };
 
+        // labels of the previous diagonal run are finished one iteration late, so that the s1/s2 loads
+        // (issued when the run was found) never stall the next code lookup
+        bool pend = false;
+        bool pend_mine = false;
+        uint32_t pend_run = 0, pend_pos = 0;
+        int pend_a = 0, pend_b = 0;
+        auto finish_pending = [&]() {
+            if (!pend) return;
+            const uint32_t op = (pend_a == pend_b) ? 0u : 1u;
+            const uint32_t mmask = __ballot_sync(0xffffffffu, pend_mine && op == 0u);
+            n_match += (uint32_t)__popc(mmask);
+            n_mis += pend_run - (uint32_t)__popc(mmask);
+            if (pend_mine) ops[pend_pos + (uint32_t)lane] = (uint8_t)op;
+            pend = false;
+        };
+
+        unsigned long long dbg_iters = 0, dbg_reloads = 0;
+        const long long dbg_t0 = clock64();
         if (i == 0 && j == 0) {
             // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
             if (lane == 0) ops[0] = 0;
@@ -118,24 +135,30 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             n_match = 1;
         } else {
             for (;;) {
+                dbg_iters++;
                 uint32_t c0 = cell_code(i, j);
                 if (c0 == 7u) {
-                    // (re)load the window that ends at this cell: lanes [l-7, l] x rows [r-127, r] of its tile
+                    dbg_reloads++;
+                    // (re)load the window that ends at this row: rows [r-255, r] x all 32 fill-lanes of the tile
                     const uint32_t jj = j - 1, ii = i - 1;
-                    const uint32_t s = jj / G::W, l = (jj % G::W) / K;
-                    const uint32_t p = ii >> PANEL_H_LOG2, r = ii & (PANEL_H - 1);
-                    wp = p; ws = s;
-                    wl1 = l; wl0 = (l >= WL - 1) ? l - (WL - 1) : 0;
-                    wr1 = r; wr0 = (r >= WR - 1) ? r - (WR - 1) : 0;
-                    wc0 = (wr0 + wl0) / SPC;
-                    const uint32_t cmax = (wr1 + wl1) / SPC;
+                    wp = ii >> PANEL_H_LOG2;
+                    ws = jj / G::W;
+                    wr1 = ii & (PANEL_H - 1);
+                    wr0 = (wr1 >= WR - 1) ? wr1 - (WR - 1) : 0;
+                    wc0 = wr0 / SPC;
+                    const uint32_t nch = (wr1 + 31) / SPC - wc0 + 1;   // <= NCH
                     const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
-                                                                         (uint64_t)(p * pd->S + s) * pd->tile_code_bytes);
+                                                                         (uint64_t)(wp * pd->S + ws) * pd->tile_code_bytes) +
+                                        (size_t)wc0 * 32 + lane;
                     __syncwarp();
-                    for (uint32_t x = lane; x < WL * NCH; x += 32) {
-                        const uint32_t a = x / NCH, b = x % NCH;
-                        const uint32_t ch = wc0 + b, fl = wl0 + a;
-                        if (fl <= wl1 && ch <= cmax) win[x] = __ldcs(tile + (size_t)ch * 32 + fl);
+                    {
+                        // asynchronous global -> shared copies: all chunks in flight at once, one memory latency per window
+                        uint32_t dst = smem_u32(win + lane);
+                        for (uint32_t b = 0; b < nch; ++b) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)b * 32) : "memory");
+                            dst += 32 * 16;
+                        }
+                        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
                     }
                     __syncwarp();
                     c0 = cell_code(i, j);
@@ -151,24 +174,28 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 const uint32_t same = __ballot_sync(0xffffffffu, cx == c0);
                 const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
                 const bool mine = x < run;
-                uint32_t op;
                 if (c0 == 0u) {
-                    const int a = (ci < m) ? (int)__ldg(s1 + ci) : -1;   // is_match(i, j): Option<u8>, None == None
-                    const int b = (cj < n) ? (int)__ldg(s2 + cj) : -1;
-                    op = (a == b) ? 0u : 1u;
-                    const uint32_t mm = __ballot_sync(0xffffffffu, mine && op == 0u);
-                    n_match += (uint32_t)__popc(mm);
-                    n_mis += run - (uint32_t)__popc(mm);
+                    // is_match(i, j): Option<u8> equality, None == None (sequence.rs:113-114); consumed next iteration
+                    const int a = (mine && ci < m) ? (int)__ldg(s1 + ci) : -1;
+                    const int b = (mine && cj < n) ? (int)__ldg(s2 + cj) : -1;
+                    finish_pending();
+                    pend = true;
+                    pend_mine = mine;
+                    pend_run = run;
+                    pend_pos = nops;
+                    pend_a = a;
+                    pend_b = b;
                     last = 0u;
                 } else {
+                    finish_pending();
                     const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
                     const bool opens = (last != ext);                  // algo.rs:373-379, 388-394
-                    op = (x == 0 && opens) ? ext + 2u : ext;           // OpenInsert = 4, OpenDelete = 5
+                    const uint32_t op = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
                     n_open += opens ? 1u : 0u;
                     n_ext += opens ? run - 1u : run;
                     last = ext;
+                    if (mine) ops[nops + x] = (uint8_t)op;
                 }
-                if (mine) ops[nops + x] = (uint8_t)op;
                 nops += run;
                 // last emitted cell, then the checked_sub move (algo.rs:412-417); run cells are all inside the table
                 res.end_i = i - (run - 1u) * di;
@@ -179,6 +206,11 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 j = j_none ? 0u : j - run * dj;
                 if (i == 0 && j == 0) break;
             }
+            finish_pending();
+        }
+        if (P.debug) {
+            res.lcs_at_first_max = dbg_iters | (dbg_reloads << 32);
+            res.fill_ms = (double)(clock64() - dbg_t0);
         }
         res.n_ops = nops;
         res.matches = n_match;

@@ -1,0 +1,16 @@
+import os, sys
+os.environ["GX_WALK_STATS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, bench
+import genomics_rs_b200 as gx
+from genomics_rs_b200 import _lib
+_lib.ensure_init(0)
+w = bench.build_workload("corona45", 0, 1, 0)
+plan = gx.Plan(w["len1"], w["len2"], bench.SCORES, False, traceback=True)
+plan.upload(w["blob"], w["off1"], w["off2"]); plan.execute(); plan.execute()
+res, ops, off = plan.fetch()
+print("walk_ms", plan.walk_ms)
+for q in np.argsort(-res["fill_ms"])[:6].tolist() + np.argsort(res["fill_ms"])[:2].tolist():
+    it = int(res["lcs_at_first_max"][q]) & 0xffffffff; rl = int(res["lcs_at_first_max"][q]) >> 32
+    cyc = res["fill_ms"][q]
+    print(f"pair {q}: ops {int(res['n_ops'][q])} opens {int(res['opening_gaps'][q])} iters {it} reloads {rl} cycles {cyc:.0f} = {cyc/1.963e6:.3f} ms, {cyc/max(it,1):.0f} cyc/iter")
