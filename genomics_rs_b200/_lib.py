@@ -21,6 +21,8 @@ EXPORTS = [
     "gx_init", "gx_shutdown", "gx_device_count", "gx_strerror", "gx_last_error", "gx_version", "gx_check_scores",
     "gx_align_pair", "gx_align_batch", "gx_score_batch", "gx_plan_create", "gx_plan_upload", "gx_plan_execute",
     "gx_plan_fetch", "gx_plan_fetch_scores", "gx_plan_destroy", "gx_plan_stat", "gx_replay_ops", "gx_k0_measure",
+    "gx_band_range", "gx_band_create", "gx_band_export", "gx_band_connect", "gx_band_upload", "gx_band_execute",
+    "gx_band_score", "gx_band_stat", "gx_band_destroy", "gx_nw_score_banded",
 ]
 
 
@@ -85,6 +87,17 @@ def load() -> C.CDLL:
         lib.gx_plan_stat.argtypes = [vp, i32]; lib.gx_plan_stat.restype = C.c_double
         lib.gx_replay_ops.argtypes = [vp, u64, u64, u64, vp, vp]; lib.gx_replay_ops.restype = i32
         lib.gx_k0_measure.argtypes = [vp, i32]; lib.gx_k0_measure.restype = i32
+        lib.gx_band_range.argtypes = [u64, i32, i32, C.POINTER(u64), C.POINTER(u64)]; lib.gx_band_range.restype = i32
+        lib.gx_band_create.argtypes = [u64, u64, i32, i32, i32, GxScores, C.POINTER(vp)]; lib.gx_band_create.restype = i32
+        lib.gx_band_export.argtypes = [vp, vp, u64]; lib.gx_band_export.restype = i32
+        lib.gx_band_connect.argtypes = [vp, vp, vp]; lib.gx_band_connect.restype = i32
+        lib.gx_band_upload.argtypes = [vp, vp, vp]; lib.gx_band_upload.restype = i32
+        lib.gx_band_execute.argtypes = [vp]; lib.gx_band_execute.restype = i32
+        lib.gx_band_score.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(i32)]; lib.gx_band_score.restype = i32
+        lib.gx_band_stat.argtypes = [vp, i32]; lib.gx_band_stat.restype = C.c_double
+        lib.gx_band_destroy.argtypes = [vp]; lib.gx_band_destroy.restype = None
+        lib.gx_nw_score_banded.argtypes = [vp, u64, vp, u64, GxScores, i32, C.POINTER(C.c_int64)]
+        lib.gx_nw_score_banded.restype = i32
         _lib = lib
     return _lib
 

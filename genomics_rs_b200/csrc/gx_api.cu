@@ -17,7 +17,7 @@
 namespace gx {
 
 static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
-static_assert(sizeof(PairDesc) == 80, "PairDesc layout");
+static_assert(sizeof(PairDesc) == 104, "PairDesc layout");
 static_assert(warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
               "per-warp smem must keep 16 B alignment");
 
@@ -39,7 +39,7 @@ struct Ctx {
 };
 
 static Ctx *g_ctx = nullptr;
-static std::mutex g_mu;
+static std::recursive_mutex g_mu;   // recursive: the gx_band_* entry points call the gx_plan_* ones
 static thread_local std::string g_err;
 
 static int fail_cuda(cudaError_t e, const char *what) {
@@ -108,6 +108,7 @@ enum PlanKind { KIND_WAVEFRONT = 0, KIND_READS = 1 };
 
 }  // namespace gx
 
+struct gx_band;
 struct gx_plan {
     gx::Ctx *ctx = nullptr;
     int kind = gx::KIND_WAVEFRONT;
@@ -150,6 +151,23 @@ struct gx_plan {
     int launches = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0, dev_bytes = 0;
     std::vector<uint8_t> ops_stage;
+    // band plans (gx_band_*): every "pair" is a column band of one wide table
+    gx_band *band = nullptr;
+};
+
+// One process's share of a column-banded table: bands [first,last) of n_bands, linked left to right.
+struct gx_band {
+    gx_plan *plan = nullptr;
+    uint64_t m = 0, n_total = 0;
+    gx_scores sc{};
+    int n_bands = 0, first = 0, last = 0;
+    std::vector<uint64_t> col0, width;        // of the local bands
+    uint8_t *link = nullptr;                  // own link block (plain cudaMalloc, exportable): [ack 256 B][inbox 8 B x m]
+    std::vector<unsigned long long *> internal;   // inbox of local band q+1 == outbox of local band q
+    void *left_base = nullptr, *right_base = nullptr;   // opened IPC mappings of the neighbours' link blocks
+    uint32_t epoch = 0;                       // executes finished
+    bool connected = false, poisoned = false, trivial = false;
+    float fill_ms = 0;
 };
 
 namespace gx {
@@ -258,7 +276,7 @@ int gx_device_count(void) {
 }
 
 int gx_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         cudaGetLastError();
@@ -289,7 +307,7 @@ int gx_init(int device) {
 }
 
 void gx_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaStreamSynchronize(g_ctx->stream);
@@ -325,9 +343,12 @@ int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
-                   gx_plan **out) {
-    std::lock_guard<std::mutex> lk(g_mu);
+}  // extern "C"
+
+// band_col0 != null: the "pairs" are consecutive column bands of one table (band q starts at column band_col0[q]);
+// their strips are ticketed as one left-to-right sequence and the short-read kernel is never chosen.
+static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
+                              const uint64_t *band_col0, gx_plan **out) {
     if (!out) return GX_ERR_ARG;
     *out = nullptr;
     if (!g_ctx) return GX_ERR_NOT_INIT;
@@ -361,7 +382,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
     for (uint64_t q = 0; q < n_pairs; ++q) pl->cells += (len1[q] + 1) * (len2[q] + 1);
 
     // short-read batches without traceback go to the inter-task kernel (K4)
-    const bool reads = !pl->traceback && pl->track != 2 && n_pairs >= 1024 && max_len <= (uint64_t)READS_MAX_LEN &&
+    const bool reads = !band_col0 && !pl->traceback && pl->track != 2 && n_pairs >= 1024 && max_len <= (uint64_t)READS_MAX_LEN &&
                        (!is_local || sc.s_mismatch < 0);
     pl->kind = reads ? KIND_READS : KIND_WAVEFRONT;
     int rc = GX_OK;
@@ -419,6 +440,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
     std::vector<TileDesc> tiles;
     std::vector<uint64_t> keys;
     uint64_t colbuf = 0, top = 0, codes = 0, ops = 0, progress = 0, best = 0;
+    uint64_t strip_base = 0;   // band plans: strips of all bands form one sequence
     for (uint64_t q = 0; q < n_pairs; ++q) {
         PairDesc &pd = pl->pairs[q];
         memset(&pd, 0, sizeof pd);
@@ -436,6 +458,7 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
         pd.tile_base = (uint32_t)best;
         const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
         pd.tile_code_bytes = interior ? tile_batches(rows_max, BATCH) * CPB * 32 * 16 : 0;
+        pd.col0 = band_col0 ? (uint32_t)band_col0[q] : 0u;
         if (interior) {
             colbuf += (uint64_t)(pd.S - 1) * m;
             top += n;
@@ -452,8 +475,9 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
         for (uint32_t p = 0; p < pd.P; ++p)
             for (uint32_t s = 0; s < pd.S; ++s) {
                 tiles.push_back({(uint32_t)q, p, s, 0});
-                keys.push_back(((uint64_t)p * PANEL_H + (uint64_t)s * 64) << 24 | (q & 0xffffff));
+                keys.push_back(((uint64_t)p * PANEL_H + (strip_base + s) * 64) << 24 | (q & 0xffffff));
             }
+        if (band_col0) strip_base += pd.S;
     }
     {
         std::vector<uint32_t> idx(tiles.size());
@@ -498,8 +522,16 @@ int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
     return GX_OK;
 }
 
+extern "C" {
+
+int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
+                   gx_plan **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    return plan_create_locked(len1, len2, n_pairs, sc, is_local, flags, nullptr, out);
+}
+
 int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *off2) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!blob && blob_len) || ((!off1 || !off2) && pl->n_pairs)) return GX_ERR_ARG;
     Ctx *c = pl->ctx;
     CK(cudaSetDevice(c->device));
@@ -566,7 +598,7 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
 }
 
 int gx_plan_execute(gx_plan *pl) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl) return GX_ERR_ARG;
     if (!pl->uploaded) return GX_ERR_ARG;
     Ctx *c = pl->ctx;
@@ -605,9 +637,21 @@ int gx_plan_execute(gx_plan *pl) {
         return GX_OK;
     }
 
+    gx_band *bd = pl->band;
+    if (bd && bd->poisoned) {
+        g_err = "band plan is unusable after a failed execute (neighbouring bands are out of step): create it again";
+        return GX_ERR_INTERNAL;
+    }
     CK(cudaEventRecord(c->ev[0], c->stream));   // the step's device time includes its own control-word reset
-    if (pl->colbuf_dirty && pl->colbuf_entries) {
-        CK(cudaMemsetAsync(pl->d_colbuf, 0xff, pl->colbuf_entries * 8, c->stream));  // parity bit 1 everywhere
+    if (pl->colbuf_dirty) {
+        if (pl->colbuf_entries) CK(cudaMemsetAsync(pl->d_colbuf, 0xff, pl->colbuf_entries * 8, c->stream));  // parity bit 1 everywhere
+        if (bd) {
+            if (bd->epoch != 0 && bd->n_bands > bd->last - bd->first) {   // a remote neighbour cannot be rewound
+                bd->poisoned = true;
+                return GX_ERR_INTERNAL;
+            }
+            for (auto *lk : bd->internal) CK(cudaMemsetAsync(lk, 0xff, bd->m * 8, c->stream));
+        }
         pl->parity = 0;
     }
     pl->colbuf_dirty = true;  // until this execute completes
@@ -630,6 +674,7 @@ int gx_plan_execute(gx_plan *pl) {
     fp.tiles = pl->d_tiles;
     fp.n_tiles = (uint32_t)pl->n_tiles;
     fp.parity = pl->parity;
+    fp.epoch = bd ? bd->epoch + 1 : 0;
     fp.ticket = pl->d_ctrl;
     fp.progress = pl->d_ctrl + 16;
     fp.colbuf = pl->d_colbuf;
@@ -647,6 +692,11 @@ int gx_plan_execute(gx_plan *pl) {
         pl->launches++;
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
+    if (bd && bd->left_base) {   // our inbox is consumed: the left neighbour may start its next execute
+        gx_band_ack_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<uint32_t *>(bd->left_base), bd->epoch + 1);
+        CK(cudaGetLastError());
+        pl->launches++;
+    }
     WalkParams wp;
     wp.blob = pl->d_blob;
     wp.pairs = pl->d_pairs;
@@ -676,8 +726,10 @@ int gx_plan_execute(gx_plan *pl) {
     CK(cudaStreamSynchronize(c->stream));
     if (abort_word) {
         g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";
+        if (bd && bd->n_bands > bd->last - bd->first) bd->poisoned = true;
         return GX_ERR_INTERNAL;
     }
+    if (bd) bd->epoch++;
     CK(cudaEventElapsedTime(&pl->fill_ms, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&pl->walk_ms, c->ev[1], c->ev[2]));
     pl->parity ^= 1u;
@@ -687,7 +739,7 @@ int gx_plan_execute(gx_plan *pl) {
 }
 
 int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!out && pl->n_pairs)) return GX_ERR_ARG;
     if (!pl->executed) return GX_ERR_ARG;
     if (pl->traceback && pl->n_pairs && (!ops_blob || !ops_off)) return GX_ERR_ARG;
@@ -736,7 +788,7 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
 }
 
 int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!scores && pl->n_pairs)) return GX_ERR_ARG;
     if (!pl->executed) return GX_ERR_ARG;
     Ctx *c = pl->ctx;
@@ -779,10 +831,232 @@ double gx_plan_stat(const gx_plan *pl, int what) {
 }
 
 void gx_plan_destroy(gx_plan *pl) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl) return;
     plan_release(pl);
     delete pl;
+}
+
+
+// ================================================================================================
+// Column-banded single pair (BASELINE config 5): SURVEY.md 8e.  Score only, global.
+// ================================================================================================
+int gx_band_range(uint64_t n_total, int n_bands, int band, uint64_t *col0, uint64_t *width) {
+    if (n_bands < 1 || band < 0 || band >= n_bands || !col0 || !width) return GX_ERR_ARG;
+    // wide tables: band edges on multiples of 512 columns (a whole strip for every K); narrow ones: even split
+    uint64_t lo, hi;
+    if (n_total / (uint64_t)n_bands >= std::max<uint64_t>(4096, 512ull * n_bands)) {
+        const uint64_t base = ((n_total + n_bands - 1) / n_bands + 511) / 512 * 512;
+        lo = std::min<uint64_t>(n_total, base * band);
+        hi = std::min<uint64_t>(n_total, base * (band + 1));
+    } else {
+        const uint64_t q = n_total / n_bands, r = n_total % n_bands;
+        lo = q * band + std::min<uint64_t>(band, r);
+        hi = lo + q + ((uint64_t)band < r ? 1 : 0);
+    }
+    *col0 = lo;
+    *width = hi - lo;
+    return GX_OK;
+}
+
+static void band_free(gx_band *b) {
+    if (!b) return;
+    if (b->plan) gx_plan_destroy(b->plan);
+    if (g_ctx) {
+        for (auto *p : b->internal) pool_free(g_ctx, p);
+        if (b->left_base) cudaIpcCloseMemHandle(b->left_base);
+        if (b->right_base) cudaIpcCloseMemHandle(b->right_base);
+        if (b->link) cudaFree(b->link);
+        cudaGetLastError();
+    }
+    delete b;
+}
+
+int gx_band_create(uint64_t m, uint64_t n_total, int n_bands, int first_band, int last_band, gx_scores sc, gx_band **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!out) return GX_ERR_ARG;
+    *out = nullptr;
+    if (!g_ctx) return GX_ERR_NOT_INIT;
+    if (n_bands < 1 || first_band < 0 || last_band <= first_band || last_band > n_bands) return GX_ERR_ARG;
+    int rc = check_scores_impl(sc, m, n_total, false);
+    if (rc) return rc;
+    if (m > 0 && n_total > 0 && n_total < (uint64_t)n_bands) return GX_ERR_ARG;   // every band needs a column
+    Ctx *c = g_ctx;
+    CK(cudaSetDevice(c->device));
+    gx_band *b = new (std::nothrow) gx_band();
+    if (!b) return GX_ERR_NOMEM;
+    b->m = m;
+    b->n_total = n_total;
+    b->sc = sc;
+    b->n_bands = n_bands;
+    b->first = first_band;
+    b->last = last_band;
+    b->trivial = (m == 0 || n_total == 0);   // boundary-only table: the score is a formula (algo.rs:204-220)
+    if (b->trivial) {
+        *out = b;
+        return GX_OK;
+    }
+    const int nl = last_band - first_band;
+    std::vector<uint64_t> l1(nl, m), l2(nl);
+    b->col0.resize(nl);
+    b->width.resize(nl);
+    for (int q = 0; q < nl; ++q) {
+        gx_band_range(n_total, n_bands, first_band + q, &b->col0[q], &b->width[q]);
+        l2[q] = b->width[q];
+        if (l2[q] == 0) {
+            delete b;
+            return GX_ERR_ARG;
+        }
+    }
+    rc = plan_create_locked(l1.data(), l2.data(), (uint64_t)nl, sc, 0, 0, b->col0.data(), &b->plan);
+    if (rc) {
+        delete b;
+        return rc;
+    }
+    b->plan->band = b;
+    for (int q = 0; q + 1 < nl && rc == GX_OK; ++q) {
+        unsigned long long *p = nullptr;
+        rc = pool_alloc(c, m * 8, (void **)&p);
+        if (rc == GX_OK) b->internal.push_back(p);
+    }
+    if (rc == GX_OK && nl < n_bands) {
+        // remote neighbours: our link block holds the inbox of our first band and the ack word of our last band
+        cudaError_t e = cudaMalloc((void **)&b->link, 256 + m * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(b->link, 0xff, 256 + m * 8, c->stream);   // parity bit 1 everywhere
+        if (e == cudaSuccess) e = cudaMemsetAsync(b->link, 0, 256, c->stream);              // ack = 0 executes finished
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = (e == cudaErrorMemoryAllocation) ? GX_ERR_NOMEM : fail_cuda(e, "band link block");
+        }
+    }
+    if (rc != GX_OK) {
+        band_free(b);
+        return rc;
+    }
+    // pointers known now: internal links; remote ones are patched in by gx_band_connect
+    for (int q = 0; q < nl; ++q) {
+        PairDesc &pd = b->plan->pairs[q];
+        pd.inbox = (q > 0) ? b->internal[q - 1] : nullptr;
+        pd.outbox = (q + 1 < nl) ? b->internal[q] : nullptr;
+        pd.ack = nullptr;
+    }
+    b->connected = (nl == n_bands);
+    *out = b;
+    return GX_OK;
+}
+
+int gx_band_export(gx_band *b, void *handle, uint64_t handle_cap) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b || !handle || handle_cap < GX_BAND_HANDLE_BYTES) return GX_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= GX_BAND_HANDLE_BYTES, "handle size");
+    memset(handle, 0, GX_BAND_HANDLE_BYTES);
+    if (!b->link) return GX_OK;   // nothing to share (all bands local, or a boundary-only table)
+    CK(cudaSetDevice(g_ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, b->link));
+    memcpy(handle, &h, sizeof h);
+    return GX_OK;
+}
+
+int gx_band_connect(gx_band *b, const void *left_handle, const void *right_handle) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b) return GX_ERR_ARG;
+    if (b->trivial) return GX_OK;
+    const bool need_left = b->first > 0, need_right = b->last < b->n_bands;
+    if ((need_left && !left_handle) || (need_right && !right_handle)) return GX_ERR_ARG;
+    if (b->connected) return GX_OK;
+    CK(cudaSetDevice(g_ctx->device));
+    const int nl = b->last - b->first;
+    if (need_left) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, left_handle, sizeof h);
+        CK(cudaIpcOpenMemHandle(&b->left_base, h, cudaIpcMemLazyEnablePeerAccess));
+        b->plan->pairs[0].inbox = reinterpret_cast<const unsigned long long *>(b->link + 256);
+    }
+    if (need_right) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, right_handle, sizeof h);
+        CK(cudaIpcOpenMemHandle(&b->right_base, h, cudaIpcMemLazyEnablePeerAccess));
+        b->plan->pairs[nl - 1].outbox = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(b->right_base) + 256);
+        b->plan->pairs[nl - 1].ack = reinterpret_cast<const uint32_t *>(b->link);
+    }
+    b->connected = true;
+    if (b->plan->uploaded) {
+        CK(cudaMemcpyAsync(b->plan->d_pairs, b->plan->pairs.data(), nl * sizeof(PairDesc), cudaMemcpyHostToDevice, g_ctx->stream));
+        CK(cudaStreamSynchronize(g_ctx->stream));
+    }
+    return GX_OK;
+}
+
+int gx_band_upload(gx_band *b, const uint8_t *s1, const uint8_t *s2) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b) return GX_ERR_ARG;
+    if (b->trivial) return GX_OK;
+    if (!s1 || !s2) return GX_ERR_ARG;
+    const int nl = b->last - b->first;
+    const uint64_t c_lo = b->col0[0], c_hi = b->col0[nl - 1] + b->width[nl - 1];
+    std::vector<uint8_t> blob(b->m + (c_hi - c_lo));
+    memcpy(blob.data(), s1, b->m);
+    memcpy(blob.data() + b->m, s2 + c_lo, c_hi - c_lo);
+    std::vector<uint64_t> off1(nl, 0), off2(nl);
+    for (int q = 0; q < nl; ++q) off2[q] = b->m + (b->col0[q] - c_lo);
+    return gx_plan_upload(b->plan, blob.data(), blob.size(), off1.data(), off2.data());
+}
+
+int gx_band_execute(gx_band *b) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b) return GX_ERR_ARG;
+    if (b->trivial) return GX_OK;
+    if (!b->connected) return GX_ERR_ARG;
+    int rc = gx_plan_execute(b->plan);
+    b->fill_ms = b->plan->fill_ms;
+    return rc;
+}
+
+int gx_band_score(gx_band *b, int64_t *score, int *valid) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!b || !score || !valid) return GX_ERR_ARG;
+    *valid = (b->last == b->n_bands) ? 1 : 0;
+    *score = 0;
+    if (!*valid) return GX_OK;
+    if (b->trivial) {   // algo.rs:195-220: only boundary cells exist
+        const uint64_t len = b->m + b->n_total;
+        *score = len ? (int64_t)b->sc.h + (int64_t)len * b->sc.g : 0;
+        return GX_OK;
+    }
+    if (!b->plan->executed) return GX_ERR_ARG;
+    const int nl = b->last - b->first;
+    std::vector<int64_t> sc(nl);
+    int rc = gx_plan_fetch_scores(b->plan, sc.data());
+    if (rc) return rc;
+    *score = sc[nl - 1];
+    return GX_OK;
+}
+
+double gx_band_stat(const gx_band *b, int what) {
+    if (!b) return -1.0;
+    if (what == 16) return (double)b->epoch;
+    if (!b->plan) return what == 3 ? (double)((b->m + 1) * (b->n_total + 1)) : 0.0;
+    return gx_plan_stat(b->plan, what);
+}
+
+void gx_band_destroy(gx_band *b) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    band_free(b);
+}
+
+int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score) {
+    if (!score || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
+    gx_band *b = nullptr;
+    int rc = gx_band_create(m, n, n_bands, 0, n_bands, sc, &b);
+    if (rc) return rc;
+    int valid = 0;
+    rc = gx_band_upload(b, s1, s2);
+    if (!rc) rc = gx_band_execute(b);
+    if (!rc) rc = gx_band_score(b, score, &valid);
+    gx_band_destroy(b);
+    return rc;
 }
 
 int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,

@@ -32,7 +32,14 @@ struct PairDesc {
     uint32_t progress_off;     // u32 entries: progress[s] = panels finished by strip s
     uint32_t tile_base;        // tile_best index of tile (0,0); tile (p,s) at tile_base + p*S + s
     uint32_t tile_code_bytes;
-    uint32_t pad_;
+    uint32_t col0;             // column band (config 5): this "pair" is columns col0+1 .. col0+n of a wider table
+    // band links: strip 0 takes its left boundary from `inbox` (rows 1..m at [i-1]) instead of the column-0
+    // formula; the last strip publishes its right boundary to `outbox`, which may be peer-GPU memory (NVLink).
+    const unsigned long long *inbox;
+    unsigned long long *outbox;
+    // flow control of a remote outbox: the consumer stores the number of executes it has finished here (our memory);
+    // execute e may overwrite the consumer's inbox only once *ack >= e-1.  Null when the outbox is local or absent.
+    const uint32_t *ack;
 };
 
 struct TileDesc {
@@ -54,6 +61,7 @@ struct FillParams {
     const TileDesc *tiles;
     uint32_t n_tiles;
     uint32_t parity;                 // LL parity bit of this execute (SURVEY "boundary hand-off")
+    uint32_t epoch;                  // 1-based execute number of a band plan (see PairDesc::ack), else 0
     uint32_t *ticket;
     uint32_t *progress;
     unsigned long long *colbuf;
@@ -118,6 +126,23 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// system-scope variants: band hand-off between GPUs (peer memory over NVLink); data and flag share one word
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;

@@ -83,7 +83,9 @@ struct Geo {
 __host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_t batch) { return (rows + 31 + batch - 1) / batch; }
 
 // One batch of BATCH systolic steps of one warp.
-template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD>
+// THRU (last strip of a column band whose width is not a multiple of the strip): padding columns pass (E,I) of
+// the band's last real column through unchanged, so that lane 31 still publishes the band's right boundary.
+template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool THRU = false>
 __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int &elast, int &ilast, int &vd,
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
                                           const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
@@ -153,8 +155,13 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                     eu[k] = En;
                     du[k] = Dn;
                 }
-                e = En;
-                irun = In;
+                if (THRU) {
+                    e = (k < kvalid) ? En : e;
+                    irun = (k < kvalid) ? In : irun;
+                } else {
+                    e = En;
+                    irun = In;
+                }
                 if (TRACK == 2) {
                     int key = (Vn << KB) | k;
                     if (PAD) key = (k < kvalid) ? key : -1;
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         const int jl = s * W + lane * K;  // columns jl+1 .. jl+K (1-based) belong to this lane
         const int kvalid = min(max(n - jl, 0), K);
         const bool has_pad = (s + 1) * W > n;
+        const int col0 = (int)pd->col0;
 
         // ---- stage s1[i0 .. i0+rows) with a TMA bulk copy (16-byte aligned window around it)
         const uint8_t *s1g = seq + pd->s1_off + i0;
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         if (p == 0) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                eu[k] = (LOCAL ? 0 : h + (jl + k + 1) * g) + hg;  // algo.rs:213-220 (row 0), V = insert_score
+                eu[k] = (LOCAL ? 0 : h + (col0 + jl + k + 1) * g) + hg;  // algo.rs:213-220 (row 0), V = insert_score
                 du[k] = NEG32;
             }
         } else {
@@ -293,20 +301,27 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
                 du[k] = v.y;
             }
         }
-        const unsigned long long *cb_in = (s > 0) ? P.colbuf + pd->colbuf_off + (uint64_t)(s - 1) * m + i0 : nullptr;
-        unsigned long long *cb_out = (s < S - 1) ? P.colbuf + pd->colbuf_off + (uint64_t)s * m + i0 : nullptr;
+        // left boundary: previous strip's column buffer, or the band inbox (written by the neighbouring band / GPU)
+        const bool left_band = (s == 0) && (pd->inbox != nullptr);
+        const bool right_band = (s == S - 1) && (pd->outbox != nullptr);
+        const unsigned long long *cb_in =
+            (s > 0) ? P.colbuf + pd->colbuf_off + (uint64_t)(s - 1) * m + i0 : (left_band ? pd->inbox + i0 : nullptr);
+        unsigned long long *cb_out =
+            (s < S - 1) ? P.colbuf + pd->colbuf_off + (uint64_t)s * m + i0 : (right_band ? pd->outbox + i0 : nullptr);
+        const bool has_left = cb_in != nullptr;
+        auto ld_bnd = [&](const unsigned long long *q) { return left_band ? ld_relaxed_sys_u64(q) : ld_relaxed_u64(q); };
 
         // ---- diagonal seed: E of (row i0, column jl)
         int vd = __shfl_up_sync(FULL, eu[K - 1], 1);
         if (lane == 0) {
-            if (s == 0) {
+            if (!has_left) {
                 vd = ((p == 0) ? 0 : (LOCAL ? 0 : h + i0 * g)) + hg;      // algo.rs:195-211 (column 0)
             } else if (p == 0) {
-                vd = (LOCAL ? 0 : h + jl * g) + hg;                       // row 0
+                vd = (LOCAL ? 0 : h + (col0 + jl) * g) + hg;              // row 0
             } else {
                 unsigned long long v;
                 uint32_t spins = 0;
-                while ((((uint32_t)((v = ld_relaxed_u64(cb_in - 1)) >> 32)) & 1u) != parity) {
+                while ((((uint32_t)((v = ld_bnd(cb_in - 1)) >> 32)) & 1u) != parity) {
                     if (spin_check(spins, abort_word)) {
                         dead = true;
                         break;
@@ -314,6 +329,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
                     __nanosleep(100);
                 }
                 vd = (int)(uint32_t)v;
+            }
+        }
+        // remote outbox: the neighbouring GPU must have finished consuming the previous execute before row 1 of
+        // this one overwrites its inbox (the consumer's stream stores its finished-execute count into pd->ack)
+        if (right_band && p == 0 && pd->ack != nullptr && lane == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_sys_u32(pd->ack) + 1u < P.epoch) {
+                if (spin_check(spins, abort_word)) {
+                    dead = true;
+                    break;
+                }
+                __nanosleep(2000);
             }
         }
         dead = __any_sync(FULL, dead);
@@ -330,14 +357,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         unsigned long long nxt = 0;
         auto issue = [&](uint32_t bt) {
             const int r = (int)(B * bt) + lane;
-            if (s > 0 && lane < B && r < rows) nxt = ld_relaxed_u64(cb_in + r);
+            if (has_left && lane < B && r < rows) nxt = ld_bnd(cb_in + r);
         };
-        if (s > 0 && P.start_lead > 0) {
+        if (has_left && P.start_lead > 0) {
             // slack: do not start before the left neighbour is start_lead rows into this panel
             const int lead = min((int)P.start_lead, rows - 1);
             uint32_t spins = 0;
             const long long w0 = P.stats ? clock64() : 0;
-            while ((((uint32_t)(ld_relaxed_u64(cb_in + lead) >> 32)) & 1u) != parity) {
+            while ((((uint32_t)(ld_bnd(cb_in + lead) >> 32)) & 1u) != parity) {
                 if (spin_check(spins, abort_word)) {
                     dead = true;
                     break;
@@ -376,7 +403,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
             {
                 uint2 cur;
                 const int rb = t0 + lane;
-                if (s == 0) {
+                if (!has_left) {
                     cur.x = (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
                     cur.y = (uint32_t)NEG32;
                 } else {
@@ -393,7 +420,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
                         }
                         // not there yet: fall back far enough that the next batches find their data ready
                         __nanosleep(spins == 1 ? 1500 : 300);
-                        if (!ok) nxt = ld_relaxed_u64(cb_in + rb);
+                        if (!ok) nxt = ld_bnd(cb_in + rb);
                     }
                     if (P.stats && spins) st_bnd += clock64() - w0;
                     if (dead) break;
@@ -407,7 +434,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
 
             const bool full = (t0 >= 31) && (t0 + B - 1 <= rows - 1);
             uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
-            if (full) {
+            bool thru = false;
+            if constexpr (!LOCAL && !CODES && TRACK == 0) {
+                if (right_band && has_pad) {
+                    thru = true;
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, true, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                               one, s1base, prof_lane, inring, outring, cdst, t0,
+                                                                               rows, lane, kvalid);
+                }
+            }
+            if (thru) {
+            } else if (full) {
                 if ((TRACK != 0) && has_pad)
                     run_batch<K, LOCAL, CODES, TRACK, PROF, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
                                                                          one, s1base, prof_lane, inring, outring, cdst, t0,
@@ -430,7 +467,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
                     const uint2 v = outring[lane];
                     const unsigned long long packed =
                         (unsigned long long)v.x | ((unsigned long long)((v.y << 1) | parity) << 32);
-                    st_relaxed_u64(cb_out + ro, packed);
+                    if (right_band) st_relaxed_sys_u64(cb_out + ro, packed);
+                    else st_relaxed_u64(cb_out + ro, packed);
                 }
             }
             // (the __syncwarp of the next settle orders these out-ring reads before lane 31 writes again)
@@ -489,5 +527,9 @@ __global__ void __launch_bounds__(256) gx_encode_kernel(const uint8_t *__restric
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = lut[in[i]];
 }
+
+// Band flow control: tells the left neighbour (its memory, possibly over NVLink) that execute `epoch` of this
+// band has consumed its inbox completely.  Stream-ordered after the fill kernel.
+__global__ void gx_band_ack_kernel(uint32_t *peer_ack, uint32_t epoch) { st_release_sys_u32(peer_ack, epoch); }
 
 }  // namespace gx

@@ -128,6 +128,33 @@ void gx_plan_destroy(gx_plan *plan);
  * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch) */
 double gx_plan_stat(const gx_plan *plan, int what);
 
+/* ---- one very long pair, global, score only, cut into column bands (BASELINE config 5).
+ * Replaces alignment_table (algo.rs:151-282) for tables whose 48-byte cells could never exist (1 Mbp x 1 Mbp).
+ * The (m+1) x (n+1) table is cut into n_bands column bands (gx_band_range).  Band b hands the (E,I) of its last
+ * column, 8 bytes per row, to band b+1 with the same flag-less 64-bit protocol the strips inside a band use.
+ * A process owns the contiguous bands [first_band, last_band) on its GPU:
+ *   all bands in one process      -> one kernel, nothing to connect (also the way to test N ranks on one GPU);
+ *   one band (or range) per GPU   -> each process exports a 64-byte handle of its link block (CUDA IPC), the
+ *                                    handles are exchanged by the caller (any transport; the Python host uses
+ *                                    torch.distributed), and gx_band_connect maps the neighbours' blocks: the fill
+ *                                    kernel of band b then stores its boundary rows straight into GPU b+1's HBM
+ *                                    over NVLink and GPU b+1's kernel polls its own memory.  No host round trip,
+ *                                    no collective call on the data path.
+ * All processes must call gx_band_execute the same number of times; the score lives on the owner of the last band. */
+#define GX_BAND_HANDLE_BYTES 64
+typedef struct gx_band gx_band;
+int gx_band_range(uint64_t n_total, int n_bands, int band, uint64_t *col0, uint64_t *width);   /* pure host arithmetic */
+int gx_band_create(uint64_t m, uint64_t n_total, int n_bands, int first_band, int last_band, gx_scores sc, gx_band **band);
+int gx_band_export(gx_band *band, void *handle, uint64_t handle_cap);     /* handle_cap >= GX_BAND_HANDLE_BYTES */
+int gx_band_connect(gx_band *band, const void *left_handle, const void *right_handle);  /* NULL where there is no neighbour */
+int gx_band_upload(gx_band *band, const uint8_t *s1, const uint8_t *s2);  /* full s1 (m bytes), full s2 (n_total bytes) */
+int gx_band_execute(gx_band *band);                                       /* synchronous; device time in gx_band_stat(b,0) */
+int gx_band_score(gx_band *band, int64_t *score, int *valid);             /* valid = 1 on the owner of the last band */
+double gx_band_stat(const gx_band *band, int what);                       /* as gx_plan_stat; 16 = executes finished */
+void gx_band_destroy(gx_band *band);
+/* all bands on this process's GPU: create + upload + execute + score + destroy */
+int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score);
+
 /* ---- replay helper: expands ops into (i,j) per entry exactly as algo.rs:412-417 would have pushed them. */
 int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t start_j,
                   uint32_t *ops_i, uint32_t *ops_j);

@@ -23,6 +23,8 @@
  *   gxo_score_linear    score (and local last-argmax) only, O(n) memory.
  *   gxo_score_batch     gxo_score_linear over a blob of pairs (pthread parallel-for).
  *   gxo_nw_score_blocked multi-threaded global score for very long pairs.
+ *   gxo_nw_band         one column band of a global table with an explicit left boundary
+ *                       column (checker of the multi-GPU column-band decomposition).
  *
  * Reference type/function map
  *   cell_t           <- AlignmentCell            algo.rs:25-35
@@ -490,6 +492,46 @@ int gxo_nw_score_blocked(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint6
     }
     *score = Vr[n];
     free(Vr); free(Dr); free(Vc); free(Ic); free(corner);
+    return 0;
+}
+
+/* One column band of the global table: columns col0+1 .. col0+nb of s2 (s2band = s2 + col0), all m rows.
+ * Same recurrences as gxo_score_linear (algo.rs:221-265).  The left boundary is column col0 of the full
+ * table: for col0 == 0 the column-0 formulas of algo.rs:195-211 (in_V/in_I ignored, may be NULL), otherwise
+ * in_V[i-1], in_I[i-1] = V and insert_score of cell (i, col0), i = 1..m, as produced by the band to the left.
+ * Row 0 is algo.rs:213-220 at absolute column col0+j.  out_V/out_I (m entries, may be NULL) receive column
+ * col0+nb; *score = V[m][col0+nb].  Exact int64. */
+int gxo_nw_band(const uint8_t *s1, uint64_t m, const uint8_t *s2band, uint64_t nb, uint64_t col0,
+                int64_t a, int64_t b, int64_t g, int64_t h,
+                const int64_t *in_V, const int64_t *in_I, int64_t *out_V, int64_t *out_I, int64_t *score) {
+    if (!(h <= 0 && g < 0 && h + g < 0)) return 4;
+    if (col0 > 0 && (!in_V || !in_I) && m > 0) return 5;
+    const int64_t hg = h + g;
+    int64_t *V = (int64_t *)malloc((nb + 1) * sizeof(int64_t));
+    int64_t *D = (int64_t *)malloc((nb + 1) * sizeof(int64_t));
+    if (!V || !D) { free(V); free(D); return 2; }
+    V[0] = col0 ? h + (int64_t)col0 * g : 0;                       /* V[0][col0] */
+    D[0] = NEG64;
+    for (uint64_t j = 1; j <= nb; j++) { V[j] = h + (int64_t)(col0 + j) * g; D[j] = NEG64; }
+    for (uint64_t i = 1; i <= m; i++) {
+        int64_t vdiag = V[0];
+        int64_t I;
+        if (col0 == 0) { V[0] = h + (int64_t)i * g; I = NEG64; }    /* algo.rs:204-211 */
+        else { V[0] = in_V[i - 1]; I = in_I[i - 1]; }
+        int64_t vleft = V[0];
+        uint8_t c1 = s1[i - 1];
+        for (uint64_t j = 1; j <= nb; j++) {
+            int64_t In = max2(I + g, vleft + hg);
+            int64_t Dn = max2(D[j] + g, V[j] + hg);
+            int64_t Sn = vdiag + ((c1 == s2band[j - 1]) ? a : b);
+            int64_t Vn = max2(max2(In, Dn), Sn);
+            vdiag = V[j]; V[j] = Vn; D[j] = Dn; I = In; vleft = Vn;
+        }
+        if (out_V) out_V[i - 1] = vleft;
+        if (out_I) out_I[i - 1] = I;
+    }
+    if (score) *score = V[nb];
+    free(V); free(D);
     return 0;
 }
 

@@ -89,6 +89,9 @@ def _bind(lib):
     lib.gxo_nw_score_blocked.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int, C.c_uint64, i64p]
     lib.gxo_nw_score_blocked.restype = C.c_int
+    lib.gxo_nw_band.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64p]
+    lib.gxo_nw_band.restype = C.c_int
     lib.gxo_hash_ops.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.gxo_hash_ops.restype = C.c_uint64
     lib.gxo_sizeof_result.restype = C.c_uint64
@@ -187,6 +190,25 @@ def nw_score_blocked(s1, s2, scores, n_threads: int = 8, blk: int = 4096) -> int
     if rc:
         raise RuntimeError(f"oracle blocked status {rc}")
     return int(sc.value)
+
+
+def nw_band(s1, s2_band, col0: int, scores, left=None):
+    """One column band (columns col0+1 .. col0+len(s2_band)) of the global table.
+    left = (V, I) int64 arrays of column col0 (rows 1..m), or None for col0 == 0.
+    -> (score at the band's bottom-right cell, (V, I) of the band's last column)"""
+    a1, a2 = _bytes(s1), _bytes(s2_band)
+    m = a1.size
+    out_v, out_i = np.zeros(m, np.int64), np.zeros(m, np.int64)
+    if left is not None:
+        in_v, in_i = np.ascontiguousarray(left[0], np.int64), np.ascontiguousarray(left[1], np.int64)
+        assert in_v.size == m and in_i.size == m
+    sc = C.c_int64()
+    rc = lib().gxo_nw_band(_ptr(a1), m, _ptr(a2), a2.size, int(col0), *[int(x) for x in scores],
+                           _ptr(in_v) if left is not None else None, _ptr(in_i) if left is not None else None,
+                           _ptr(out_v), _ptr(out_i), C.byref(sc))
+    if rc:
+        raise RuntimeError(f"oracle band status {rc}")
+    return int(sc.value), (out_v, out_i)
 
 
 def hash_ops(ops: np.ndarray, start: Tuple[int, int]) -> int:
