@@ -105,6 +105,7 @@ static void pool_free(Ctx *c, void *p) {
 
 // ------------------------------------------------------------------------------------------------
 enum PlanKind { KIND_WAVEFRONT = 0, KIND_READS = 1 };
+typedef void (*FillKernel)(const FillParams);
 
 }  // namespace gx
 
@@ -116,11 +117,13 @@ struct gx_plan {
     gx_scores sc{};
     int is_local = 0, flags = 0;
     int K = 8;
+    bool chain1 = false;               // latency-optimised recurrence (gx_fill.cuh, CHAIN1)
     int track = 0;
     bool traceback = false;
     std::vector<gx::PairDesc> pairs;   // host copy (offsets filled at upload)
     std::vector<uint64_t> len1, len2;
     uint64_t n_tiles = 0;
+    uint64_t n_strips = 0;             // strips of all pairs at the chosen K
     uint64_t cells = 0;
     uint64_t code_bytes = 0, ops_bytes = 0, colbuf_entries = 0, top_entries = 0, progress_entries = 0, best_entries = 0;
     uint64_t blob_cap = 0;
@@ -131,6 +134,7 @@ struct gx_plan {
     uint8_t *d_lut = nullptr;
     unsigned long long *d_stats = nullptr;   // GX_FILL_STATS=1: wait/tile cycle counters of the last execute
     unsigned long long h_stats[8] = {0};
+    unsigned long long *d_timeline = nullptr;   // GX_FILL_STATS=2: per-tile timestamps (debug)
     bool prof = false;
     gx::PairDesc *d_pairs = nullptr;
     gx::TileDesc *d_tiles = nullptr;
@@ -172,36 +176,42 @@ struct gx_band {
 
 namespace gx {
 
+// the fill kernels are instantiated in gx_fill_inst.cu, one translation unit per (K, CHAIN1) so that they build in parallel
+FillKernel pick_fill_4_0(bool prof, bool L, bool C, int track);
+FillKernel pick_fill_4_1(bool prof, bool L, bool C, int track);
+FillKernel pick_fill_8_0(bool prof, bool L, bool C, int track);
+FillKernel pick_fill_8_1(bool prof, bool L, bool C, int track);
+FillKernel pick_fill_16_0(bool prof, bool L, bool C, int track);
+FillKernel pick_fill_16_1(bool prof, bool L, bool C, int track);
+template <int K>
+static FillKernel pick_fill(bool prof, bool chain1, bool L, bool C, int track) {
+    if (K == 4) return chain1 ? pick_fill_4_1(prof, L, C, track) : pick_fill_4_0(prof, L, C, track);
+    if (K == 8) return chain1 ? pick_fill_8_1(prof, L, C, track) : pick_fill_8_0(prof, L, C, track);
+    return chain1 ? pick_fill_16_1(prof, L, C, track) : pick_fill_16_0(prof, L, C, track);
+}
+
 template <int K>
 static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
     Ctx *c = pl->ctx;
-    const size_t smem = (size_t)WARPS_PER_CTA * warp_smem_bytes(K);
     void (*kern)(const FillParams) = nullptr;
     const bool L = pl->is_local != 0, C = pl->traceback;
-    if (pl->prof) {
-        if (!L && !C) kern = gx_fill_kernel<K, false, false, 0, true>;
-        else if (!L && C) kern = gx_fill_kernel<K, false, true, 0, true>;
-        else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1, true>;
-        else if (L && !C) kern = gx_fill_kernel<K, true, false, 2, true>;
-        else kern = gx_fill_kernel<K, true, true, 2, true>;
-    } else {
-        if (!L && !C) kern = gx_fill_kernel<K, false, false, 0, false>;
-        else if (!L && C) kern = gx_fill_kernel<K, false, true, 0, false>;
-        else if (L && !C && pl->track == 1) kern = gx_fill_kernel<K, true, false, 1, false>;
-        else if (L && !C) kern = gx_fill_kernel<K, true, false, 2, false>;
-        else kern = gx_fill_kernel<K, true, true, 2, false>;
-    }
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern = pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
+    // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
+    int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * WARPS_PER_SM) ? WARPS_PER_CTA : 1;
+    if (const char *e = getenv("GX_WPC")) wpc = atoi(e) == 1 ? 1 : WARPS_PER_CTA;
+    const size_t smem = (size_t)wpc * warp_smem_bytes(K);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * warp_smem_bytes(K))));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
     if (occ < 1) occ = 1;
-    uint64_t want = (pl->n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    occ = std::min(occ, WARPS_PER_SM / wpc);
+    uint64_t want = (pl->n_tiles + wpc - 1) / wpc;
     uint64_t cap = (uint64_t)c->sm_count * occ;
     if (getenv("GX_GRID_CAP")) grid_cap = atoi(getenv("GX_GRID_CAP"));
     if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
     int grid = (int)std::min<uint64_t>(want, cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, CTA_THREADS, smem, c->stream>>>(fp);
+    kern<<<grid, wpc * 32, smem, c->stream>>>(fp);
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -228,7 +238,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
+    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -421,7 +431,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     // ---- wavefront geometry: K columns per lane.  Larger K amortises the per-step hand-off over more cells,
     // smaller K gives more strips (warps) for batches that cannot fill the GPU otherwise.
     {
-        const uint64_t resident = (uint64_t)c->sm_count * 2 * WARPS_PER_CTA;
+        const uint64_t resident = (uint64_t)c->sm_count * WARPS_PER_SM;
         uint64_t strips16 = 0, strips8 = 0;
         for (uint64_t q = 0; q < n_pairs; ++q)
             if (len1[q] && len2[q]) {
@@ -433,6 +443,16 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
             const int k = atoi(e);
             if (k == 4 || k == 8 || k == 16) pl->K = k;
         }
+        // latency-optimised recurrence (one more ALU op per cell, 1-op row chain) when warps are too few to hide the
+        // classic 3-op chain: measured win below ~1/4 of the resident warps, loss at full occupancy
+        {
+            uint64_t strips = 0;
+            for (uint64_t q = 0; q < n_pairs; ++q)
+                if (len1[q] && len2[q]) strips += (len2[q] + 32 * pl->K - 1) / (32 * pl->K);
+            pl->chain1 = strips * 4 < resident;
+            pl->n_strips = strips;
+        }
+        if (const char *e = getenv("GX_CHAIN1")) pl->chain1 = atoi(e) != 0;
     }
     const int K = pl->K, W = 32 * K;
     const uint32_t SPC = 64u / (uint32_t)K, BATCH = SPC > 8 ? SPC : 8, CPB = BATCH / SPC;
@@ -661,6 +681,8 @@ int gx_plan_execute(gx_plan *pl) {
     fp.blob_sym = pl->prof ? pl->d_blob_sym : nullptr;
     fp.one = 1u;
     fp.stats = nullptr;
+    fp.timeline = nullptr;
+    fp.poll_nap = getenv("GX_POLL_NAP") ? (uint32_t)atoi(getenv("GX_POLL_NAP")) : 0u;
     fp.start_lead = getenv("GX_START_LEAD") ? (uint32_t)atoi(getenv("GX_START_LEAD")) : 0u;
     if (getenv("GX_FILL_STATS")) {
         if (!pl->d_stats) {
@@ -669,6 +691,13 @@ int gx_plan_execute(gx_plan *pl) {
         }
         CK(cudaMemsetAsync(pl->d_stats, 0, 64, c->stream));
         fp.stats = pl->d_stats;
+        if (atoi(getenv("GX_FILL_STATS")) >= 2) {
+            if (!pl->d_timeline) {
+                int rc = pool_alloc(c, (pl->n_tiles + 1) * 32, (void **)&pl->d_timeline);
+                if (rc) return rc;
+            }
+            fp.timeline = pl->d_timeline;
+        }
     }
     fp.pairs = pl->d_pairs;
     fp.tiles = pl->d_tiles;
@@ -811,6 +840,14 @@ int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) {
     return GX_OK;
 }
 
+int gx_plan_debug_timeline(gx_plan *pl, uint64_t *out, uint64_t cap_words) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!pl || !out || !pl->d_timeline || cap_words < pl->n_tiles * 4) return GX_ERR_ARG;
+    CK(cudaSetDevice(pl->ctx->device));
+    CK(cudaMemcpy(out, pl->d_timeline, pl->n_tiles * 32, cudaMemcpyDeviceToHost));
+    return GX_OK;
+}
+
 double gx_plan_stat(const gx_plan *pl, int what) {
     if (!pl) return -1.0;
     switch (what) {
@@ -825,6 +862,7 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 8: return (double)pl->n_tiles;
         case 9: return (double)pl->kind;
         case 15: return (double)pl->K;
+        case 17: return pl->chain1 ? 1.0 : 0.0;
         case 10: case 11: case 12: case 13: case 14: return (double)pl->h_stats[what - 10];
         default: return -1.0;
     }

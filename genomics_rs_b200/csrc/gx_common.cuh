@@ -11,8 +11,14 @@ constexpr int NEG32 = -(1 << 30);
 // Rows of one panel: a tile is (panel p, strip s) = PANEL_H rows x 32*K columns, owned by one warp.
 constexpr int PANEL_H_LOG2 = 12;
 constexpr int PANEL_H = 1 << PANEL_H_LOG2;
+// The fill kernel has no CTA-level cooperation (per-warp shared memory, no __syncthreads), so the same code runs as
+// 8-warp CTAs (2 per SM) or as single-warp CTAs (16 per SM).  Single-warp CTAs let the block scheduler spread a small
+// number of busy warps over all SMs instead of packing the first tickets onto the few SMs whose CTAs started first;
+// with every warp slot busy the 8-warp shape is a few per cent faster.  gx_api.cu picks the shape per plan.
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int CTAS_PER_SM = 2;    // at 8 warps: 128 registers per thread
+constexpr int WARPS_PER_SM = WARPS_PER_CTA * CTAS_PER_SM;
 
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
 // the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.
@@ -68,7 +74,9 @@ struct FillParams {
     int2 *top;
     uint8_t *codes;
     int4 *tile_best;
+    uint32_t poll_nap;               // ns a strip sleeps between two polls of its left boundary (0: poll back to back)
     uint32_t start_lead;             // rows of extra lead a strip waits for before its first batch (slack against convoys)
+    unsigned long long *timeline;    // optional with stats: 4 words per tile (debug)
     unsigned long long *stats;       // optional (null in production): [0] top-wait, [1] boundary-wait, [2] tile, [3] s1-wait cycles, [4] tiles
     int g, hg, ap, bp, h;            // ap = s_match - (h+g), bp = s_mismatch - (h+g): S is formed in E-space (E = V + h + g)
 };
@@ -144,6 +152,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
 __device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -163,6 +176,19 @@ __device__ __forceinline__ void st_cg_int2(int2 *p, int2 v) {
 __device__ __forceinline__ void st_cs_uint4(uint4 *p, uint4 v) {
     // streaming store: traceback codes are written once and read only along the path
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// shared-memory load the compiler may not move or merge (pins the issue point of a deliberately early load)
+__device__ __forceinline__ uint2 lds_volatile_uint2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 template <int N>

@@ -85,16 +85,38 @@ __host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_
 // One batch of BATCH systolic steps of one warp.
 // THRU (last strip of a column band whose width is not a multiple of the strip): padding columns pass (E,I) of
 // the band's last real column through unchanged, so that lane 31 still publishes the band's right boundary.
-template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool THRU = false>
+//
+// CHAIN1 selects the latency-optimised form of the recurrence.  The classic form has a 3-instruction dependency
+// per cell along the row (I -> V -> E -> next I, 18 clk with the pipe crossing); CHAIN1 keeps everything in
+// E-space (x + h + g) and takes max(D,S) out of the chain:
+//     Sh = Ediag + sub                (S + h + g: the profile holds the raw match/mismatch scores)
+//     D' = max(D + g, Eup)            Mh = max(D' + (h+g), Sh)
+//     I' = max(I + g, Mh_left)        the only op on the row chain: 1 VIADDMNMX = 4 clk per cell
+//     E  = max(I' + (h+g), Mh)
+// (I' = max(I+g, E_left) = max(I+g, I+h+g, Mh_left) and h <= 0.)  One more ALU-pipe op per cell than the classic
+// form, 4.5x shorter chain: chosen when there are too few strips to hide latency with warps, and for score-only fills.
+template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool CHAIN1, bool THRU = false>
 __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int &elast, int &ilast, int &vd,
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
                                           const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
                                           const uint8_t *prof_lane /* profile base + lane*16 */,
                                           const uint2 *inr /* left-boundary (E,I) of this batch's steps */, uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
-                                          const int kvalid) {
+                                          const int kvalid, int (&subc)[K] /* PROF: profile row of this batch's first step in, next batch's out */) {
     using G = Geo<K>;
     constexpr int KB = G::KB;
-    const uint8_t *s1p = s1base + (t0 - lane);
+    // K < 16 (registers to spare): the s1 characters of every step of the batch (and of the next batch's first step)
+    // are fetched up front and the profile row of step+1 is fetched while step runs, so that no shared-memory
+    // latency is left on the row chain.  K = 16 lives at the 128-register limit and fetches in-step.
+    constexpr bool PIPE = K < 16;
+    int c1v[G::BATCH + 1];
+    if (PIPE) {
+#pragma unroll
+        for (int st = 0; st <= G::BATCH; ++st) {
+            const int r = t0 + st - lane;
+            if (MASKED || st == G::BATCH) c1v[st] = s1base[min(max(r, 0), rows - 1)];
+            else c1v[st] = s1base[r];
+        }
+    }
 #pragma unroll
     for (int ch = 0; ch < G::CPB; ++ch) {
         uint32_t cw[4] = {0u, 0u, 0u, 0u};
@@ -110,44 +132,70 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                 il = (int)bnd.y;
             }
             bool active = true;
-            int c1;
-            if (MASKED) {
-                active = (r >= 0) && (r < rows);
-                const int rc = min(max(r, 0), rows - 1);
-                c1 = s1base[rc];
-            } else {
-                c1 = s1p[step];
-            }
+            if (MASKED) active = (r >= 0) && (r < rows);
+            int c1 = 0;
+            if (PIPE) c1 = c1v[step];
+            else c1 = MASKED ? s1base[min(max(r, 0), rows - 1)] : s1base[r];
             int sub[K];
             if (PROF) {
-                // profile row of this row's symbol: [sym][k/4][lane][k%4] ints -> two conflict-free LDS.128
-                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
+                // profile layout [sym][k/4][lane][k%4] ints -> K/4 conflict-free LDS.128 per row
+                if (PIPE) {
+                    // this step's profile row was fetched one step ago (subc); fetch the next step's now
+#pragma unroll
+                    for (int k = 0; k < K; ++k) sub[k] = subc[k];
+                }
+                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + (PIPE ? c1v[step + 1] : c1) * (K * 128));
 #pragma unroll
                 for (int q = 0; q < K / 4; ++q) {
                     const int4 v = pp[q * 32];
-                    sub[4 * q + 0] = v.x;
-                    sub[4 * q + 1] = v.y;
-                    sub[4 * q + 2] = v.z;
-                    sub[4 * q + 3] = v.w;
+                    if (PIPE) {
+                        subc[4 * q + 0] = v.x;
+                        subc[4 * q + 1] = v.y;
+                        subc[4 * q + 2] = v.z;
+                        subc[4 * q + 3] = v.w;
+                    } else {
+                        sub[4 * q + 0] = v.x;
+                        sub[4 * q + 1] = v.y;
+                        sub[4 * q + 2] = v.z;
+                        sub[4 * q + 3] = v.w;
+                    }
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < K; ++k) sub[k] = (c1 == c2[k]) ? ap : bp;
             }
             int e = el, irun = il, ed = vd;
-            int rowbest = -1;
+            int rowbest = CHAIN1 ? INT32_MIN : -1;
+            int mh = el;   // CHAIN1: "max(D,S) of the cell to the left" -- for the lane's first column that is E_left itself
             static_for<K>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                const int In = LOCAL ? __viaddmax_s32_relu(irun, g, e) : __viaddmax_s32(irun, g, e);
-                const int Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                const int Sn = ed + sub[k];
-                const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
+                int In, Dn, En, Skey, Ikey, Vkey;   // S/I/V keys: equal keys decide the direction code; Vkey orders the local maximum
+                if (CHAIN1) {
+                    In = LOCAL ? __viaddmax_s32_relu(irun, g, mh) : __viaddmax_s32(irun, g, mh);
+                    Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
+                    const int Sh = ed + sub[k];
+                    const int Mh = __viaddmax_s32(Dn, hg, Sh);
+                    En = __viaddmax_s32(In, hg, Mh);   // local: I' >= 0 keeps E >= h+g, i.e. V >= 0
+                    if (THRU) mh = (k < kvalid) ? Mh : mh;
+                    else mh = Mh;
+                    Skey = Sh;
+                    Ikey = CODES ? In + hg : 0;
+                    Vkey = En;     // E-space: same order, same equalities
+                } else {
+                    In = LOCAL ? __viaddmax_s32_relu(irun, g, e) : __viaddmax_s32(irun, g, e);
+                    Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
+                    const int Sn = ed + sub[k];
+                    const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
+                    En = Vn + hg;
+                    Skey = Sn;
+                    Ikey = In;
+                    Vkey = Vn;
+                }
                 if (CODES) {
                     constexpr int bitpos = uu * 2 * K + 2 * k;
-                    code_acc<(1u << (bitpos & 31))>(cw[bitpos >> 5], Sn, In, Vn, one);
+                    code_acc<(1u << (bitpos & 31))>(cw[bitpos >> 5], Skey, Ikey, Vkey, one);
                 }
                 ed = eu[k];
-                const int En = Vn + hg;
                 if (MASKED) {
                     eu[k] = active ? En : eu[k];
                     du[k] = active ? Dn : du[k];
@@ -163,12 +211,12 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                     irun = In;
                 }
                 if (TRACK == 2) {
-                    int key = (Vn << KB) | k;
-                    if (PAD) key = (k < kvalid) ? key : -1;
+                    int key = (Vkey << KB) | k;
+                    if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
                     rowbest = max(rowbest, key);
                 } else if (TRACK == 1) {
-                    int key = Vn;
-                    if (PAD) key = (k < kvalid) ? key : -1;
+                    int key = Vkey;
+                    if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
                     rowbest = max(rowbest, key);
                 }
             });
@@ -191,8 +239,8 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
     }
 }
 
-template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF>
-__global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParams P) {
+template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const FillParams P) {
     using G = Geo<K>;
     constexpr int W = G::W;
     constexpr int B = G::BATCH;
@@ -213,7 +261,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
     }
     __syncwarp();
     uint32_t phase = 0;
-    const int g = P.g, hg = P.hg, ap = P.ap, bp = P.bp, h = P.h;
+    const int g = P.g, hg = P.hg, h = P.h;
+    // classic form: S = Ediag + (score - (h+g)) in V-space; CHAIN1: Sh = Ediag + score in E-space
+    const int ap = CHAIN1 ? P.ap + P.hg : P.ap, bp = CHAIN1 ? P.bp + P.hg : P.bp;
     const uint32_t one = P.one;
     const uint32_t parity = P.parity;
     uint32_t *abort_word = P.ticket + 1;
@@ -226,6 +276,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         tk = __shfl_sync(FULL, tk, 0);
         if (tk >= P.n_tiles) break;
         const long long st_t0 = P.stats ? clock64() : 0;
+        const unsigned long long tl_take = P.stats ? globaltimer_ns() : 0ull;
+        unsigned long long tl_dp0 = 0ull;
         long long st_top = 0, st_bnd = 0, st_s1 = 0;
         const TileDesc td = P.tiles[tk];
         const PairDesc *pd = P.pairs + td.pair;
@@ -283,13 +335,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
             const uint32_t *pr = P.progress + pd->progress_off + s;
             uint32_t spins = 0;
             const long long w0 = P.stats ? clock64() : 0;
-            while (ld_acquire_u32(pr) < (uint32_t)p) {
+            // poll with relaxed loads and a growing sleep (an acquire load is LDG + CCTL.IVALL: hundreds of waiting
+            // warps invalidating their SM's L1 every microsecond slow the warps that do the work), acquire once at the end
+            uint32_t nap = 100;
+            while (ld_relaxed_u32(pr) < (uint32_t)p) {
                 if (spin_check(spins, abort_word)) {
                     dead = true;
                     break;
                 }
-                __nanosleep(1000);
+                __nanosleep(nap);
+                nap = min(nap * 2u, 1000u);
             }
+            (void)ld_acquire_u32(pr);
             if (P.stats) st_top += clock64() - w0;
             if (dead) break;
             const int2 *tp = P.top + pd->top_off + jl;
@@ -309,7 +366,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         unsigned long long *cb_out =
             (s < S - 1) ? P.colbuf + pd->colbuf_off + (uint64_t)s * m + i0 : (right_band ? pd->outbox + i0 : nullptr);
         const bool has_left = cb_in != nullptr;
-        auto ld_bnd = [&](const unsigned long long *q) { return left_band ? ld_relaxed_sys_u64(q) : ld_relaxed_u64(q); };
+        auto ld_bnd = [&](const unsigned long long *q) __attribute__((always_inline)) { return left_band ? ld_relaxed_sys_u64(q) : ld_relaxed_u64(q); };
 
         // ---- diagonal seed: E of (row i0, column jl)
         int vd = __shfl_up_sync(FULL, eu[K - 1], 1);
@@ -347,7 +404,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         if (dead) break;
 
         int elast = 0, ilast = 0;
-        int best = -1, best_r = 0;
+        int best = CHAIN1 ? INT32_MIN : -1, best_r = 0;
         const uint32_t nbat = tile_batches((uint32_t)rows, B);
         uint4 *code_base = nullptr;
         if (CODES)
@@ -355,7 +412,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
 
         // ---- left boundary prefetch (LL protocol): lanes 0..B-1 fetch the entries of local rows B*bt + lane
         unsigned long long nxt = 0;
-        auto issue = [&](uint32_t bt) {
+        auto issue = [&](uint32_t bt) __attribute__((always_inline)) {
             const int r = (int)(B * bt) + lane;
             if (has_left && lane < B && r < rows) nxt = ld_bnd(cb_in + r);
         };
@@ -396,83 +453,153 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         const uint8_t *s1base = s1buf + delta;
         const uint8_t *prof_lane = prof + lane * 16;
         __syncwarp();   // profile stores visible to the whole warp
-
-        for (uint32_t bt = 0; bt < nbat; ++bt) {
-            const int t0 = (int)(B * bt);
-            // settle the B in-ring entries of this batch (rows t0 .. t0+B-1 of the left neighbour's last column)
-            {
-                uint2 cur;
-                const int rb = t0 + lane;
-                if (!has_left) {
-                    cur.x = (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
-                    cur.y = (uint32_t)NEG32;
-                } else {
-                    const bool need = (lane < B) && (rb < rows);
-                    uint32_t spins = 0;
-                    long long w0 = 0;
-                    for (;;) {
-                        const bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
-                        if (__all_sync(FULL, ok)) break;
-                        if (P.stats && spins == 0) w0 = clock64();
-                        if (__any_sync(FULL, spin_check(spins, abort_word))) {
-                            dead = true;
-                            break;
-                        }
-                        // not there yet: fall back far enough that the next batches find their data ready
-                        __nanosleep(spins == 1 ? 1500 : 300);
-                        if (!ok) nxt = ld_bnd(cb_in + rb);
-                    }
-                    if (P.stats && spins) st_bnd += clock64() - w0;
-                    if (dead) break;
-                    cur.x = (uint32_t)nxt;
-                    cur.y = (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1);
-                }
-                if (bt + 1 < nbat) issue(bt + 1);
-                if (lane < B) inring[lane] = cur;
-                __syncwarp();
+        int subc[K];    // PROF: profile row of the next step to run (software-pipelined shared-memory fetch)
+        if (PROF) {
+            const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + s1base[0] * (K * 128));
+#pragma unroll
+            for (int q = 0; q < K / 4; ++q) {
+                const int4 v = pp[q * 32];
+                subc[4 * q + 0] = v.x;
+                subc[4 * q + 1] = v.y;
+                subc[4 * q + 2] = v.z;
+                subc[4 * q + 3] = v.w;
             }
-
-            const bool full = (t0 >= 31) && (t0 + B - 1 <= rows - 1);
-            uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
-            bool thru = false;
-            if constexpr (!LOCAL && !CODES && TRACK == 0) {
-                if (right_band && has_pad) {
-                    thru = true;
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, true, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                               one, s1base, prof_lane, inring, outring, cdst, t0,
-                                                                               rows, lane, kvalid);
-                }
-            }
-            if (thru) {
-            } else if (full) {
-                if ((TRACK != 0) && has_pad)
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                         one, s1base, prof_lane, inring, outring, cdst, t0,
-                                                                         rows, lane, kvalid);
-                else
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, false>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap,
-                                                                          bp, one, s1base, prof_lane, inring, outring,
-                                                                          cdst, t0, rows, lane, kvalid);
-            } else {
-                run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0)>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                            one, s1base, prof_lane, inring, outring, cdst,
-                                                                            t0, rows, lane, kvalid);
-            }
-
-            // publish the right-boundary rows lane 31 finished in this batch: rows t0-31 .. t0+B-32
-            __syncwarp();
-            if (cb_out != nullptr && lane < B) {
-                const int ro = t0 - 31 + lane;
-                if (ro >= 0 && ro < rows) {
-                    const uint2 v = outring[lane];
-                    const unsigned long long packed =
-                        (unsigned long long)v.x | ((unsigned long long)((v.y << 1) | parity) << 32);
-                    if (right_band) st_relaxed_sys_u64(cb_out + ro, packed);
-                    else st_relaxed_u64(cb_out + ro, packed);
-                }
-            }
-            // (the __syncwarp of the next settle orders these out-ring reads before lane 31 writes again)
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) subc[k] = 0;
         }
+
+        // ---- batch loop, software-pipelined so that no hand-off latency sits between two batches of DP steps:
+        //   in-ring   double-buffered; the entries of batch bt+1 are settled (parity check, STS) BEFORE the DP steps of
+        //             batch bt run, their global loads were issued one batch earlier still (issue(bt+2) below);
+        //   out-ring  double-buffered; the rows lane 31 finished in batch bt are read back right after the batch and
+        //             stored to the neighbour one batch later (the LDS latency hides behind the next settle).
+        // settle(b): lanes 0..B-1 turn the prefetched word of local row B*b+lane into an in-ring entry.
+        // The common case (data already there) is branch-free apart from one vote.
+        const bool lane_b = lane < B;
+        auto settle = [&](uint32_t b) __attribute__((always_inline)) -> bool {
+            const int rb = (int)(B * b) + lane;
+            const bool need = has_left && lane_b && (rb < rows);
+            bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
+            if (!__all_sync(FULL, ok)) {
+                uint32_t spins = 0;
+                const long long w0 = P.stats ? clock64() : 0;
+                bool lost = false;
+                do {
+                    if (__any_sync(FULL, spin_check(spins, abort_word))) {
+                        lost = true;
+                        break;
+                    }
+                    // not there yet: poll again at once.  The L2 round trip (~500 clk) paces the loop, a polling warp
+                    // issues ~3 % of its scheduler's slots, and every nap here would be added to the lag of this strip
+                    // behind its left neighbour -- strips x lag is the pipeline ramp of a pair.
+                    if (P.poll_nap) __nanosleep(P.poll_nap);
+                    if (!ok) nxt = ld_bnd(cb_in + rb);
+                    ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
+                } while (!__all_sync(FULL, ok));
+                if (P.stats) st_bnd += clock64() - w0;
+                if (lost) return false;
+            }
+            uint2 cur;
+            cur.x = has_left ? (uint32_t)nxt : (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
+            cur.y = has_left ? (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1) : (uint32_t)NEG32;
+            if (lane_b) inring[(b & 1u) * B + lane] = cur;
+            return true;
+        };
+        if (!settle(0)) dead = true;
+        if (nbat > 1) issue(1);
+        __syncwarp();
+        if (P.stats) tl_dp0 = globaltimer_ns();
+        uint2 pub = make_uint2(0u, 0u);   // out-ring entry read back after the previous batch
+        int pub_row = -1;
+        auto flush_pub = [&]() __attribute__((always_inline)) {
+            if (pub_row >= 0) {
+                const unsigned long long packed =
+                    (unsigned long long)pub.x | ((unsigned long long)((pub.y << 1) | parity) << 32);
+                if (right_band) st_relaxed_sys_u64(cb_out + pub_row, packed);
+                else st_relaxed_u64(cb_out + pub_row, packed);
+            }
+        };
+        // glue around the DP steps of batch bt
+        auto pre = [&](uint32_t bt) __attribute__((always_inline)) -> bool {
+            if (bt + 1 < nbat) {
+                if (!settle(bt + 1)) return false;
+                if (bt + 2 < nbat) issue(bt + 2);
+            }
+            flush_pub();   // rows finished in batch bt-1
+            return true;
+        };
+        const bool has_out = cb_out != nullptr;
+        auto post = [&](uint32_t bt, uint2 *outr) __attribute__((always_inline)) {
+            // one barrier per batch: orders this batch's ring stores (in-ring of bt+1, out-ring of bt) before their reads
+            __syncwarp();
+            // read back the right-boundary rows lane 31 finished in this batch: rows t0-31 .. t0+B-32 (stored next batch)
+            const int ro = (int)(B * bt) - 31 + lane;
+            const bool take = has_out && lane_b && ro >= 0 && ro < rows;
+            if (take) pub = lds_volatile_uint2(outr + lane);
+            pub_row = take ? ro : -1;
+        };
+        // batches [0, nb_head) and [nb_body, nbat) touch rows outside the tile (skew) and run the masked steps;
+        // the body runs unmasked steps with straight-line glue.
+        const uint32_t nb_head = (30 + B) / B;                       // first batch with t0 >= 31
+        const uint32_t nb_body = max(nb_head, (uint32_t)rows / B);   // first batch with t0 + B - 1 > rows - 1
+        bool thru = false;
+        if constexpr (!LOCAL && !CODES && TRACK == 0) thru = right_band && has_pad;
+        // phase 0: masked head batches (all batches of a THRU tile), then the unmasked body; phase 1: masked tail.
+        // (One copy of each batch variant in the code; nothing here may end up as an out-of-line call -- the DP
+        // state lives in registers.)
+        uint32_t bt = 0;
+        for (int ph = 0; ph < 2 && !dead; ++ph) {
+            const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
+            for (; bt < m_end && !dead; ++bt) {
+                if (!pre(bt)) {
+                    dead = true;
+                    break;
+                }
+                uint2 *outr = outring + (bt & 1u) * B;
+                uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                if constexpr (!LOCAL && !CODES && TRACK == 0) {
+                    if (thru)
+                        run_batch<K, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                                           one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
+                                                                                           (int)(B * bt), rows, lane, kvalid, subc);
+                }
+                if (!thru)
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                                        one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
+                                                                                        (int)(B * bt), rows, lane, kvalid, subc);
+                post(bt, outr);
+            }
+            if (ph != 0 || thru || dead) continue;
+            if ((TRACK != 0) && has_pad) {
+                for (; bt < nb_body && !dead; ++bt) {
+                    if (!pre(bt)) {
+                        dead = true;
+                        break;
+                    }
+                    uint2 *outr = outring + (bt & 1u) * B;
+                    uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                                 one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
+                                                                                 (int)(B * bt), rows, lane, kvalid, subc);
+                    post(bt, outr);
+                }
+            } else {
+                for (; bt < nb_body && !dead; ++bt) {
+                    if (!pre(bt)) {
+                        dead = true;
+                        break;
+                    }
+                    uint2 *outr = outring + (bt & 1u) * B;
+                    uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
+                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
+                                                                                  (int)(B * bt), rows, lane, kvalid, subc);
+                    post(bt, outr);
+                }
+            }
+        }
+        flush_pub();
         if (dead) break;
 
         // ---- bottom row -> top buffer (next panel of this strip, and the global score)
@@ -489,11 +616,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
         if (TRACK != 0) {
             int bv, bi, bj;
             if (TRACK == 2) {
-                bv = (best < 0) ? -1 : (best >> KB);
+                if (CHAIN1) bv = (kvalid == 0) ? -1 : (best >> KB) - hg;   // keys were taken in E-space
+                else bv = (best < 0) ? -1 : (best >> KB);
                 bi = i0 + best_r + 1;
                 bj = jl + (best & (K - 1)) + 1;
             } else {
-                bv = best;
+                if (CHAIN1) bv = (kvalid == 0) ? -1 : best - hg;
+                else bv = best;
                 bi = 0;
                 bj = 0;
             }
@@ -515,12 +644,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) gx_fill_kernel(const FillParam
             atomicAdd(P.stats + 2, (unsigned long long)(clock64() - st_t0));
             atomicAdd(P.stats + 3, (unsigned long long)st_s1);
             atomicAdd(P.stats + 4, 1ull);
+            if (P.timeline) {   // per tile: ticket taken, first DP step, end (ns), pair/p/s and SM
+                unsigned long long *tl = P.timeline + 4ull * tk;
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                tl[0] = tl_take;
+                tl[1] = tl_dp0;
+                tl[2] = globaltimer_ns();
+                tl[3] = ((unsigned long long)td.pair << 48) | ((unsigned long long)p << 32) | ((unsigned long long)s << 12) | smid;
+            }
         }
     }
 }
 
 // Re-encodes sequence bytes to dense symbols through a 256-entry table (PROF path): sym 0..3, 255 = not in alphabet.
-__global__ void __launch_bounds__(256) gx_encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
+static __global__ void __launch_bounds__(256) gx_encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
                                                         const uint8_t *__restrict__ lut256) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = lut256[threadIdx.x];
@@ -530,6 +668,6 @@ __global__ void __launch_bounds__(256) gx_encode_kernel(const uint8_t *__restric
 
 // Band flow control: tells the left neighbour (its memory, possibly over NVLink) that execute `epoch` of this
 // band has consumed its inbox completely.  Stream-ordered after the fill kernel.
-__global__ void gx_band_ack_kernel(uint32_t *peer_ack, uint32_t epoch) { st_release_sys_u32(peer_ack, epoch); }
+static __global__ void gx_band_ack_kernel(uint32_t *peer_ack, uint32_t epoch) { st_release_sys_u32(peer_ack, epoch); }
 
 }  // namespace gx

@@ -127,6 +127,8 @@ void gx_plan_destroy(gx_plan *plan);
  * 3 cells (sum (m+1)(n+1)), 4 traceback bytes written per execute, 5 device bytes held by the plan,
  * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch) */
 double gx_plan_stat(const gx_plan *plan, int what);
+/* debug (GX_FILL_STATS=2): per tile {ticket ns, first DP step ns, end ns, pair<<48|panel<<32|strip<<12|sm}; cap_words >= 4 * tiles */
+int gx_plan_debug_timeline(gx_plan *plan, uint64_t *out, uint64_t cap_words);
 
 /* ---- one very long pair, global, score only, cut into column bands (BASELINE config 5).
  * Replaces alignment_table (algo.rs:151-282) for tables whose 48-byte cells could never exist (1 Mbp x 1 Mbp).
