@@ -469,11 +469,9 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
             for (int k = 0; k < K; ++k) subc[k] = 0;
         }
 
-        // ---- batch loop, software-pipelined so that no hand-off latency sits between two batches of DP steps:
-        //   in-ring   double-buffered; the entries of batch bt+1 are settled (parity check, STS) BEFORE the DP steps of
-        //             batch bt run, their global loads were issued one batch earlier still (issue(bt+2) below);
-        //   out-ring  double-buffered; the rows lane 31 finished in batch bt are read back right after the batch and
-        //             stored to the neighbour one batch later (the LDS latency hides behind the next settle).
+        // ---- batch loop.  The hand-off rings are double-buffered (the global load of batch bt+2's left boundary is in
+        //      flight while batch bt computes), and every batch ends with: publish its finished right-boundary rows,
+        //      then settle the in-ring of the next batch (post() below).
         // settle(b): lanes 0..B-1 turn the prefetched word of local row B*b+lane into an in-ring entry.
         // The common case (data already there) is branch-free apart from one vote.
         const bool lane_b = lane < B;
@@ -520,24 +518,25 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
                 else st_relaxed_u64(cb_out + pub_row, packed);
             }
         };
-        // glue around the DP steps of batch bt
-        auto pre = [&](uint32_t bt) __attribute__((always_inline)) -> bool {
-            if (bt + 1 < nbat) {
-                if (!settle(bt + 1)) return false;
-                if (bt + 2 < nbat) issue(bt + 2);
-            }
-            flush_pub();   // rows finished in batch bt-1
-            return true;
-        };
+        // glue after the DP steps of batch bt.  Order matters for the lag of a strip behind its left neighbour
+        // (strips x lag is the pipeline ramp of a pair): the in-ring of batch bt+1 is settled only now, just in time,
+        // and the rows finished in batch bt are published before anything else can block.
         const bool has_out = cb_out != nullptr;
-        auto post = [&](uint32_t bt, uint2 *outr) __attribute__((always_inline)) {
-            // one barrier per batch: orders this batch's ring stores (in-ring of bt+1, out-ring of bt) before their reads
-            __syncwarp();
-            // read back the right-boundary rows lane 31 finished in this batch: rows t0-31 .. t0+B-32 (stored next batch)
+        auto post = [&](uint32_t bt, uint2 *outr) __attribute__((always_inline)) -> bool {
+            // rows lane 31 finished in this batch: t0-31 .. t0+B-32
             const int ro = (int)(B * bt) - 31 + lane;
             const bool take = has_out && lane_b && ro >= 0 && ro < rows;
+            __syncwarp();                                    // out-ring stores of this batch -> visible
             if (take) pub = lds_volatile_uint2(outr + lane);
             pub_row = take ? ro : -1;
+            flush_pub();
+            pub_row = -1;
+            if (bt + 1 < nbat) {
+                if (!settle(bt + 1)) return false;           // may wait for the left neighbour
+                if (bt + 2 < nbat) issue(bt + 2);
+                __syncwarp();                                // in-ring stores of batch bt+1 -> visible
+            }
+            return true;
         };
         // batches [0, nb_head) and [nb_body, nbat) touch rows outside the tile (skew) and run the masked steps;
         // the body runs unmasked steps with straight-line glue.
@@ -552,10 +551,6 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
         for (int ph = 0; ph < 2 && !dead; ++ph) {
             const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
             for (; bt < m_end && !dead; ++bt) {
-                if (!pre(bt)) {
-                    dead = true;
-                    break;
-                }
                 uint2 *outr = outring + (bt & 1u) * B;
                 uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
                 if constexpr (!LOCAL && !CODES && TRACK == 0) {
@@ -568,34 +563,26 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
                     run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
                                                                                         one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
                                                                                         (int)(B * bt), rows, lane, kvalid, subc);
-                post(bt, outr);
+                if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
             if ((TRACK != 0) && has_pad) {
                 for (; bt < nb_body && !dead; ++bt) {
-                    if (!pre(bt)) {
-                        dead = true;
-                        break;
-                    }
                     uint2 *outr = outring + (bt & 1u) * B;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
                     run_batch<K, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
                                                                                  (int)(B * bt), rows, lane, kvalid, subc);
-                    post(bt, outr);
+                    if (!post(bt, outr)) dead = true;
                 }
             } else {
                 for (; bt < nb_body && !dead; ++bt) {
-                    if (!pre(bt)) {
-                        dead = true;
-                        break;
-                    }
                     uint2 *outr = outring + (bt & 1u) * B;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
                     run_batch<K, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
                                                                                   one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
                                                                                   (int)(B * bt), rows, lane, kvalid, subc);
-                    post(bt, outr);
+                    if (!post(bt, outr)) dead = true;
                 }
             }
         }
