@@ -803,7 +803,7 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
     const bool walk_dbg = getenv("GX_WALK_STATS") != nullptr;
     for (uint64_t q = 0; q < pl->n_pairs; ++q) {
         if (!walk_dbg) out[q].fill_ms = pl->fill_ms;
-        out[q].walk_ms = pl->walk_ms;
+        if (!walk_dbg) out[q].walk_ms = pl->walk_ms;
         if (pl->traceback) {
             const uint64_t cap = ops_off[q + 1] - ops_off[q];
             if (out[q].n_ops > cap) {

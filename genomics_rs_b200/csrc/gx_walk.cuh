@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
         constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
         constexpr int NCH = (WR + 32 + SPC - 1) / SPC + 1;    // code chunks per fill-lane in a window
         __shared__ uint4 win[NCH * 32];                       // [chunk][fill-lane]
+        // label characters of the window: is_match(i,j) reads s1[i] and s2[j] (0-based: the characters AFTER the
+        // cell's own, algo.rs:354), i.e. s1[i0w+1 .. ] for the window's rows and s2[j0w+1 .. ] for the strip's columns
+        __shared__ uint8_t s1w[WR + 32];
+        __shared__ uint8_t s2w[G::W + 32];
+        uint32_t s1w0 = 0, s2w0 = 0;                          // sequence index of s1w[0] / s2w[0]
         uint8_t *ops = P.ops + pd->ops_off;
         uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
         uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
@@ -110,23 +115,8 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             return (w32[bitpos >> 5] >> (bitpos & 31u)) & 3u;
         };
 
-        // labels of the previous diagonal run are finished one iteration late, so that the s1/s2 loads
-        // (issued when the run was found) never stall the next code lookup
-        bool pend = false;
-        bool pend_mine = false;
-        uint32_t pend_run = 0, pend_pos = 0;
-        int pend_a = 0, pend_b = 0;
-        auto finish_pending = [&]() {
-            if (!pend) return;
-            const uint32_t op = (pend_a == pend_b) ? 0u : 1u;
-            const uint32_t mmask = __ballot_sync(0xffffffffu, pend_mine && op == 0u);
-            n_match += (uint32_t)__popc(mmask);
-            n_mis += pend_run - (uint32_t)__popc(mmask);
-            if (pend_mine) ops[pend_pos + (uint32_t)lane] = (uint8_t)op;
-            pend = false;
-        };
-
         unsigned long long dbg_iters = 0, dbg_reloads = 0;
+        long long dbg_reload_cyc = 0;
         const long long dbg_t0 = clock64();
         if (i == 0 && j == 0) {
             // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
@@ -139,6 +129,7 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 uint32_t c0 = cell_code(i, j);
                 if (c0 == 7u) {
                     dbg_reloads++;
+                    const long long dbg_r0 = P.debug ? clock64() : 0;
                     // (re)load the window that ends at this row: rows [r-255, r] x all 32 fill-lanes of the tile
                     const uint32_t jj = j - 1, ii = i - 1;
                     wp = ii >> PANEL_H_LOG2;
@@ -158,10 +149,16 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)b * 32) : "memory");
                             dst += 32 * 16;
                         }
+                        // label characters: rows wr0..wr1 of panel wp -> s1 indices (i-1)+1, columns of strip ws -> s2 indices (j-1)+1
+                        s1w0 = (wp << PANEL_H_LOG2) + wr0 + 1u;
+                        s2w0 = ws * G::W + 1u;
+                        for (uint32_t k = (uint32_t)lane; k <= wr1 - wr0; k += 32) s1w[k] = (s1w0 + k < m) ? __ldg(s1 + s1w0 + k) : (uint8_t)0;
+                        for (uint32_t k = (uint32_t)lane; k < (uint32_t)G::W; k += 32) s2w[k] = (s2w0 + k < n) ? __ldg(s2 + s2w0 + k) : (uint8_t)0;
                         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
                     }
                     __syncwarp();
                     c0 = cell_code(i, j);
+                    if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;
                 }
                 if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
                 // every lane looks x steps ahead in the direction of c0; the run ends at the first different code
@@ -175,19 +172,17 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
                 const bool mine = x < run;
                 if (c0 == 0u) {
-                    // is_match(i, j): Option<u8> equality, None == None (sequence.rs:113-114); consumed next iteration
-                    const int a = (mine && ci < m) ? (int)__ldg(s1 + ci) : -1;
-                    const int b = (mine && cj < n) ? (int)__ldg(s2 + cj) : -1;
-                    finish_pending();
-                    pend = true;
-                    pend_mine = mine;
-                    pend_run = run;
-                    pend_pos = nops;
-                    pend_a = a;
-                    pend_b = b;
+                    // is_match(i, j): Option<u8> equality, None == None (sequence.rs:113-114).  Run cells lie in the window,
+                    // so their label characters are in s1w / s2w.
+                    const int a = (mine && ci < m) ? (int)s1w[ci - s1w0] : -1;
+                    const int b = (mine && cj < n) ? (int)s2w[cj - s2w0] : -1;
+                    const uint32_t op = (a == b) ? 0u : 1u;
+                    const uint32_t mmask = __ballot_sync(0xffffffffu, mine && op == 0u);
+                    n_match += (uint32_t)__popc(mmask);
+                    n_mis += run - (uint32_t)__popc(mmask);
+                    if (mine) ops[nops + x] = (uint8_t)op;
                     last = 0u;
                 } else {
-                    finish_pending();
                     const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
                     const bool opens = (last != ext);                  // algo.rs:373-379, 388-394
                     const uint32_t op = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
@@ -206,11 +201,11 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 j = j_none ? 0u : j - run * dj;
                 if (i == 0 && j == 0) break;
             }
-            finish_pending();
         }
         if (P.debug) {
             res.lcs_at_first_max = dbg_iters | (dbg_reloads << 32);
             res.fill_ms = (double)(clock64() - dbg_t0);
+            res.walk_ms = (double)dbg_reload_cyc;
         }
         res.n_ops = nops;
         res.matches = n_match;

@@ -13,4 +13,5 @@ print("walk_ms", plan.walk_ms)
 for q in np.argsort(-res["fill_ms"])[:6].tolist() + np.argsort(res["fill_ms"])[:2].tolist():
     it = int(res["lcs_at_first_max"][q]) & 0xffffffff; rl = int(res["lcs_at_first_max"][q]) >> 32
     cyc = res["fill_ms"][q]
-    print(f"pair {q}: ops {int(res['n_ops'][q])} opens {int(res['opening_gaps'][q])} iters {it} reloads {rl} cycles {cyc:.0f} = {cyc/1.963e6:.3f} ms, {cyc/max(it,1):.0f} cyc/iter")
+    rc = res["walk_ms"][q]
+    print(f"pair {q}: reload cycles {rc:.0f} ({rc/max(rl,1):.0f}/reload), walk-only {(cyc-rc)/max(it,1):.0f} cyc/iter; ops {int(res['n_ops'][q])} opens {int(res['opening_gaps'][q])} iters {it} reloads {rl} cycles {cyc:.0f} = {cyc/1.963e6:.3f} ms, {cyc/max(it,1):.0f} cyc/iter")
