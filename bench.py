@@ -288,7 +288,7 @@ def main():
         scores_out = np.zeros(n, np.int64)
 
         def e2e_step():
-            scores_out[:] = gx.score_batch(blob, w["off1"], w["len1"], w["off2"], w["len2"], SCORES, w["is_local"])
+            gx.score_batch(blob, w["off1"], w["len1"], w["off2"], w["len2"], SCORES, w["is_local"], out=scores_out)
         d2h = n * 4
     h2d = int(blob.size) + (n * 16 if not w["traceback"] else n * 80)
     for _ in range(min(args.warmup, 2)):
@@ -299,6 +299,10 @@ def main():
         e2e_step()
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if not w["traceback"]:
+        # the streamed host-buffer call and the resident plan must agree pair for pair
+        if not np.array_equal(scores_out, plan.fetch_scores()):
+            raise SystemExit("gx_score_batch (streamed) and the resident plan disagree")
 
     # ---- max over ranks, totals over ranks
     vals = torch.tensor([dev_ms / args.steps, wall_ms / args.steps, e2e_ms, fill_ms / args.steps, walk_ms / args.steps],

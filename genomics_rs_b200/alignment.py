@@ -283,12 +283,15 @@ def align_batch(pairs: Seq[Tuple[object, object]], scores, is_local: bool, trace
     return out
 
 
-def score_batch(blob: np.ndarray, off1, len1, off2, len2, scores, is_local: bool) -> np.ndarray:
-    """gx_score_batch: scores only (int64), the short-read workload's entry point."""
+def score_batch(blob: np.ndarray, off1, len1, off2, len2, scores, is_local: bool, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """gx_score_batch: scores only (int64), the short-read workload's entry point.
+    `out` (int64, one entry per pair) may be supplied to keep the result buffer across calls."""
     lib = _lib.ensure_init()
     blob = np.ascontiguousarray(blob, np.uint8)
     off1, len1, off2, len2 = [np.ascontiguousarray(x, np.uint64) for x in (off1, len1, off2, len2)]
-    out = np.zeros(off1.size, np.int64)
+    if out is None:
+        out = np.empty(off1.size, np.int64)
+    assert out.dtype == np.int64 and out.size == off1.size and out.flags.c_contiguous
     _lib.check(lib.gx_score_batch(blob.ctypes.data if blob.size else None, blob.size, off1.ctypes.data, len1.ctypes.data,
                                   off2.ctypes.data, len2.ctypes.data, off1.size, _scores_struct(scores), int(bool(is_local)),
                                   out.ctypes.data))

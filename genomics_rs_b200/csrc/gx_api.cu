@@ -34,6 +34,12 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<Block> pool;
+    // streamed score batches (gx_score_batch on large read sets): two lanes of copy + kernel
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_done[2] = {nullptr, nullptr};
+    int *lane_scores_host[2] = {nullptr, nullptr};   // pinned
+    uint4 *lane_rec_host[2] = {nullptr, nullptr};    // pinned: per-pair records of the chunk in flight
+    size_t lane_scores_cap = 0;
     std::string last_error;
     size_t pool_bytes = 0;
 };
@@ -312,6 +318,10 @@ int gx_init(int device) {
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->lane_done[k], cudaEventDisableTiming));
+    }
     g_ctx = c;
     return GX_OK;
 }
@@ -323,6 +333,12 @@ void gx_shutdown(void) {
     cudaStreamSynchronize(g_ctx->stream);
     for (auto &b : g_ctx->pool) cudaFree(b.ptr);
     for (auto &e : g_ctx->ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) {
+        if (g_ctx->lane_stream[k]) cudaStreamDestroy(g_ctx->lane_stream[k]);
+        if (g_ctx->lane_done[k]) cudaEventDestroy(g_ctx->lane_done[k]);
+        if (g_ctx->lane_scores_host[k]) cudaFreeHost(g_ctx->lane_scores_host[k]);
+        if (g_ctx->lane_rec_host[k]) cudaFreeHost(g_ctx->lane_rec_host[k]);
+    }
     cudaStreamDestroy(g_ctx->stream);
     delete g_ctx;
     g_ctx = nullptr;
@@ -542,6 +558,149 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     return GX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Streamed score batch: large read sets (BASELINE config 4: 10 M x 150 bp) are cut into chunks of pairs that flow
+// through two lanes (stream + device buffers each): while chunk c runs on the SMs, chunk c+1 crosses PCIe and the
+// scores of chunk c-1 come back.  The caller's arrays are used as they are (64-bit offsets and lengths, byte blob):
+// no host-side repack.  Returns GX_ERR_UNSUPPORTED when the batch does not qualify (the caller falls back to a plan).
+static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1,
+                                const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local,
+                                int64_t *scores) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!g_ctx) return GX_ERR_NOT_INIT;
+    Ctx *c = g_ctx;
+    if (n_pairs < (1u << 18) || (is_local && sc.s_mismatch >= 0)) return GX_ERR_UNSUPPORTED;
+    int rc = check_scores_impl(sc, READS_MAX_LEN, READS_MAX_LEN, is_local != 0);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const uint64_t CH = 1u << 20;   // pairs per chunk
+    if (c->lane_scores_cap < CH) {
+        for (int k = 0; k < 2; ++k) {
+            if (c->lane_scores_host[k]) cudaFreeHost(c->lane_scores_host[k]);
+            c->lane_scores_host[k] = nullptr;
+            if (c->lane_rec_host[k]) cudaFreeHost(c->lane_rec_host[k]);
+            c->lane_rec_host[k] = nullptr;
+            if (cudaHostAlloc((void **)&c->lane_scores_host[k], CH * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc((void **)&c->lane_rec_host[k], CH * sizeof(uint4), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                c->lane_scores_cap = 0;
+                return GX_ERR_NOMEM;
+            }
+        }
+        c->lane_scores_cap = CH;
+    }
+    struct Lane {
+        uint8_t *blob = nullptr;
+        size_t blob_cap = 0;
+        uint4 *rec = nullptr;
+        int *scores = nullptr;
+        uint64_t first = 0, count = 0;
+        bool busy = false;
+    } lane[2];
+    auto release = [&]() {
+        for (auto &L : lane) {
+            void *ptrs[] = {L.blob, L.rec, L.scores};
+            for (void *p : ptrs) pool_free(c, p);
+        }
+    };
+    auto drain = [&](int k) -> int {   // scores of the chunk that ran on lane k -> caller's int64 array
+        Lane &L = lane[k];
+        if (!L.busy) return GX_OK;
+        CK(cudaEventSynchronize(c->lane_done[k]));
+        const int *src = c->lane_scores_host[k];
+        int64_t *dst = scores + L.first;
+        for (uint64_t q = 0; q < L.count; ++q) dst[q] = src[q];
+        L.busy = false;
+        return GX_OK;
+    };
+    for (int k = 0; k < 2 && rc == GX_OK; ++k) {
+        Lane &L = lane[k];
+        rc = pool_alloc(c, CH * sizeof(uint4), (void **)&L.rec);
+        if (!rc) rc = pool_alloc(c, CH * 4, (void **)&L.scores);
+    }
+    for (uint64_t first = 0, ci = 0; first < n_pairs && rc == GX_OK; first += CH, ++ci) {
+        const int k = (int)(ci & 1);
+        Lane &L = lane[k];
+        const uint64_t count = std::min<uint64_t>(CH, n_pairs - first);
+        // host pass 1 over the chunk: bounds, longest sequence, byte span of the chunk in the blob (branch-free: vectorises)
+        uint64_t lo = UINT64_MAX, hi = 0, maxlen = 0, sum = 0, badbits = 0;
+        {
+            const uint64_t *o1 = off1 + first, *o2 = off2 + first, *l1 = len1 + first, *l2 = len2 + first;
+            for (uint64_t q = 0; q < count; ++q) {
+                const uint64_t a0 = o1[q], a1 = a0 + l1[q], b0 = o2[q], b1 = b0 + l2[q];
+                badbits |= (uint64_t)(a1 > blob_len) | (uint64_t)(b1 > blob_len) | (uint64_t)(a1 < a0) | (uint64_t)(b1 < b0);
+                lo = std::min(lo, std::min(a0, b0));
+                hi = std::max(hi, std::max(a1, b1));
+                maxlen = std::max(maxlen, std::max(l1[q], l2[q]));
+                sum += l1[q] + l2[q];
+            }
+        }
+        if (badbits) {
+            rc = GX_ERR_ARG;
+            break;
+        }
+        if (maxlen > (uint64_t)READS_MAX_LEN || hi - lo > 4 * sum + (1u << 20) || hi - lo >= (1ull << 32)) {
+            rc = GX_ERR_UNSUPPORTED;   // long pairs or a scattered blob: not a read stream
+            break;
+        }
+        rc = drain(k);                 // the chunk that used this lane two rounds ago
+        if (rc) break;
+        const uint64_t span = hi > lo ? hi - lo : 0;
+        if (L.blob_cap < span + 64) {
+            pool_free(c, L.blob);
+            L.blob = nullptr;
+            L.blob_cap = 0;
+            rc = pool_alloc(c, span + span / 4 + 64, (void **)&L.blob);
+            if (rc) break;
+            L.blob_cap = span + span / 4 + 64;
+        }
+        cudaStream_t st = c->lane_stream[k];
+        if (span) CK(cudaMemcpyAsync(L.blob, blob + lo, span, cudaMemcpyHostToDevice, st));
+        // host pass 2: 16-byte records relative to the chunk's first byte, written straight into pinned memory
+        // (lane k's record buffer is free: drain(k) above waited for the chunk that used it)
+        {
+            uint4 *rec = c->lane_rec_host[k];
+            const uint64_t *o1 = off1 + first, *o2 = off2 + first, *l1 = len1 + first, *l2 = len2 + first;
+            for (uint64_t q = 0; q < count; ++q)
+                rec[q] = make_uint4((uint32_t)(o1[q] - lo), (uint32_t)(o2[q] - lo), (uint32_t)l1[q], (uint32_t)l2[q]);
+        }
+        CK(cudaMemcpyAsync(L.rec, c->lane_rec_host[k], count * sizeof(uint4), cudaMemcpyHostToDevice, st));
+        ReadsParams rp;
+        rp.blob = L.blob;
+        rp.off1 = rp.off2 = nullptr;
+        rp.len1 = rp.len2 = nullptr;
+        rp.rec = L.rec;
+        rp.n_pairs = (uint32_t)count;
+        rp.scores = L.scores;
+        rp.results = nullptr;
+        rp.a = sc.s_match;
+        rp.b = sc.s_mismatch;
+        rp.g = sc.g;
+        rp.h = sc.h;
+        rp.is_local = is_local ? 1 : 0;
+        if (launch_reads(rp, (int)maxlen, c->sm_count, st) != 0) {
+            rc = GX_ERR_UNSUPPORTED;
+            break;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->lane_scores_host[k], L.scores, count * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(c->lane_done[k], st));
+        L.first = first;
+        L.count = count;
+        L.busy = true;
+    }
+    if (rc == GX_OK) rc = drain(0);
+    if (rc == GX_OK) rc = drain(1);
+    if (rc != GX_OK) {
+        cudaStreamSynchronize(c->lane_stream[0]);
+        cudaStreamSynchronize(c->lane_stream[1]);
+        cudaGetLastError();
+    }
+    release();
+    return rc;
+}
+
 extern "C" {
 
 int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
@@ -637,6 +796,7 @@ int gx_plan_execute(gx_plan *pl) {
         rp.off2 = pl->d_off2;
         rp.len1 = pl->d_len1;
         rp.len2 = pl->d_len2;
+        rp.rec = nullptr;
         rp.n_pairs = (uint32_t)pl->n_pairs;
         rp.scores = pl->d_scores;
         rp.results = nullptr;
@@ -1112,6 +1272,12 @@ int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *o
 
 int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,
                    const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int64_t *scores) {
+    if ((!seq_blob && blob_len) || ((!off1 || !len1 || !off2 || !len2 || !scores) && n_pairs)) return GX_ERR_ARG;
+    // large read sets stream through two copy/compute lanes; everything else goes through a plan
+    if (!getenv("GX_NO_STREAM")) {
+        const int rcs = score_batch_streamed(seq_blob, blob_len, off1, len1, off2, len2, n_pairs, sc, is_local, scores);
+        if (rcs != GX_ERR_UNSUPPORTED) return rcs;
+    }
     gx_plan *pl = nullptr;
     int rc = gx_plan_create(len1, len2, n_pairs, sc, is_local, 0, &pl);
     if (rc) return rc;

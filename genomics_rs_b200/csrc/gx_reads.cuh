@@ -18,15 +18,36 @@ namespace gx {
 
 constexpr int READS_MAX_LEN = 640;
 
+struct ReadsParams;
+
 struct ReadsParams {
     const uint8_t *blob;
     const uint64_t *off1, *off2;
-    const uint32_t *len1, *len2;
+    const uint32_t *len1, *len2;       // lengths as 32-bit words (plans), or null:
+    const uint4 *rec;                  // streamed chunks: one 16-byte record per pair {off1, off2, len1, len2} relative to
+                                       // `blob` (packed by the host while it validates the chunk); overrides off*/len*
     uint32_t n_pairs;
     int *scores;
     DevResult *results;   // may be null
     int a, b, g, h, is_local;
 };
+
+// geometry of pair q: sequence pointers and lengths (have == false: an empty pair at the blob's start)
+__device__ __forceinline__ void reads_pair(const ReadsParams &P, uint64_t q, bool have, const uint8_t *&s1, const uint8_t *&s2, int &m,
+                                           int &n) {
+    if (P.rec) {
+        const uint4 r = have ? __ldg(P.rec + q) : make_uint4(0u, 0u, 0u, 0u);
+        s1 = P.blob + r.x;
+        s2 = P.blob + r.y;
+        m = (int)r.z;
+        n = (int)r.w;
+    } else {
+        s1 = P.blob + (have ? P.off1[q] : 0);
+        s2 = P.blob + (have ? P.off2[q] : 0);
+        m = have ? (int)P.len1[q] : 0;
+        n = have ? (int)P.len2[q] : 0;
+    }
+}
 
 template <int G, int K, bool LOCAL>
 __global__ void __launch_bounds__(256) gx_reads_kernel(const ReadsParams P) {
@@ -43,10 +64,9 @@ __global__ void __launch_bounds__(256) gx_reads_kernel(const ReadsParams P) {
     for (uint64_t base = (uint64_t)warp_global * GPW; base < P.n_pairs; base += (uint64_t)n_warps * GPW) {
         const uint64_t q = base + gw;
         const bool have = q < P.n_pairs;
-        const int m = have ? (int)P.len1[q] : 0;
-        const int n = have ? (int)P.len2[q] : 0;
-        const uint8_t *s1 = P.blob + (have ? P.off1[q] : 0);
-        const uint8_t *s2 = P.blob + (have ? P.off2[q] : 0);
+        int m, n;
+        const uint8_t *s1, *s2;
+        reads_pair(P, q, have, s1, s2, m, n);
         const int jl = lg * K;
         int c2[K], eu[K], du[K];
 #pragma unroll
@@ -160,10 +180,10 @@ __global__ void __launch_bounds__(256, 2) gx_reads16_kernel(const ReadsParams P)
         const uint64_t dq = base + gw;
         const uint64_t qa = 2 * dq, qb = 2 * dq + 1;
         const bool ha = dq < n_dual && qa < P.n_pairs, hb = dq < n_dual && qb < P.n_pairs;
-        const int ma = ha ? (int)P.len1[qa] : 0, na = ha ? (int)P.len2[qa] : 0;
-        const int mb = hb ? (int)P.len1[qb] : 0, nb = hb ? (int)P.len2[qb] : 0;
-        const uint8_t *s1a = P.blob + (ha ? P.off1[qa] : 0), *s2a = P.blob + (ha ? P.off2[qa] : 0);
-        const uint8_t *s1b = P.blob + (hb ? P.off1[qb] : 0), *s2b = P.blob + (hb ? P.off2[qb] : 0);
+        int ma, na, mb, nb;
+        const uint8_t *s1a, *s2a, *s1b, *s2b;
+        reads_pair(P, qa, ha, s1a, s2a, ma, na);
+        reads_pair(P, qb, hb, s1b, s2b, mb, nb);
         const int jl = lg * K;
         uint32_t c2[K], vu[K], du[K];
 #pragma unroll

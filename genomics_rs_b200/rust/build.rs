@@ -8,11 +8,23 @@ fn main() {
     let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("gxalign/csrc");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = Vec::new();
-    for src in ["gx_api.cu", "gx_k0.cu"] {
-        let obj = out.join(src).with_extension("o");
+    // (source, object name, extra defines): the fill kernel is instantiated once per (K, recurrence form)
+    let mut units: Vec<(&str, String, Vec<String>)> = vec![
+        ("gx_api.cu", "gx_api.o".into(), vec![]),
+        ("gx_k0.cu", "gx_k0.o".into(), vec![]),
+    ];
+    for k in [4, 8, 16] {
+        for c in [0, 1] {
+            units.push(("gx_fill_inst.cu", format!("gx_fill_k{k}_c{c}.o"), vec![format!("-DGX_INST_K={k}"), format!("-DGX_INST_CHAIN={c}")]));
+        }
+    }
+    for (src, name, defs) in &units {
+        let obj = out.join(name);
         let ok = Command::new(&nvcc)
             .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"])
-            .args(["-Xcompiler", "-fPIC", "-c", "-o"])
+            .args(["-Xcompiler", "-fPIC"])
+            .args(defs)
+            .args(["-c", "-o"])
             .arg(&obj)
             .arg(csrc.join(src))
             .status()

@@ -205,6 +205,33 @@ def test_read_batch_scores(gx, oracle):
         assert np.array_equal(got, exp)
 
 
+def test_read_stream_scores(gx, oracle):
+    """large read sets take the streamed path of gx_score_batch (chunks of 2^20 pairs through two copy/compute lanes):
+    more than one chunk, ragged lengths, both modes, offsets that are not multiples of anything"""
+    rng = np.random.default_rng(4242)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    n_pairs = (1 << 20) + 70001
+    lens1 = rng.integers(0, 61, size=n_pairs).astype(np.uint64)
+    lens2 = rng.integers(0, 61, size=n_pairs).astype(np.uint64)
+    lens1[:4] = (0, 0, 60, 1); lens2[:4] = (0, 60, 0, 1)
+    tot = np.zeros(2 * n_pairs + 1, np.uint64)
+    inter = np.empty(2 * n_pairs, np.uint64); inter[0::2] = lens1; inter[1::2] = lens2
+    np.cumsum(inter, out=tot[1:])
+    off1, off2 = tot[0:-1:2].copy(), tot[1::2].copy()
+    blob = lut[rng.integers(0, 4, size=int(tot[-1]))]
+    # make half of the pairs similar: copy s1 into s2 where the lengths allow, then mutate a few bases
+    for q in range(0, n_pairs, 2):
+        k = int(min(lens1[q], lens2[q]))
+        if k:
+            blob[int(off2[q]):int(off2[q]) + k] = blob[int(off1[q]):int(off1[q]) + k]
+    idx = rng.integers(0, blob.size, size=blob.size // 16)
+    blob[idx] = lut[rng.integers(0, 4, size=idx.size)]
+    for is_local, scores in ((True, CONFIG_TOML), (False, TEST_CONFIG)):
+        got = gx.score_batch(blob, off1, lens1, off2, lens2, scores, is_local)
+        exp = oracle.score_batch(blob, off1, lens1, off2, lens2, scores, is_local, n_threads=8)
+        assert np.array_equal(got, exp)
+
+
 def test_large_properties(gx, oracle):
     """size-independent properties at sizes the oracle does not brute-force:
     identical sequences give m*match with an all-Match walk; transposing the pair (I <-> D) keeps the
