@@ -101,18 +101,21 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
         uint32_t wp = 0xffffffffu, ws = 0, wr0 = 0, wr1 = 0, wc0 = 0;
 
         // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (a run must end before it)
-        auto cell_code = [&](uint32_t ci, uint32_t cj) -> uint32_t {
-            if (ci == 0 && cj == 0) return 0u;            // origin: sub_score == max == 0 (algo.rs:195-202)
-            if (cj == 0) return local ? 3u : 2u;          // column 0: only delete_score is finite; local stops
-            if (ci == 0) return local ? 3u : 1u;          // row 0
-            const uint32_t jj = cj - 1, ii = ci - 1;
-            const uint32_t s = jj / G::W, l = (jj % G::W) / K, k = jj % K;
-            const uint32_t p = ii >> PANEL_H_LOG2, r = ii & (PANEL_H - 1);
-            if (!(p == wp && s == ws && r >= wr0 && r <= wr1)) return 7u;
+        // Straight-line (no branches): the lookup is on the loop-carried chain of the walk.
+        const uint32_t bnd_row0 = local ? 3u : 1u, bnd_col0 = local ? 3u : 2u;
+        auto cell_code = [&](uint32_t ci, uint32_t cj) __attribute__((always_inline)) -> uint32_t {
+            const uint32_t jj = cj - 1u, ii = ci - 1u;            // wrap to 0xffffffff on the boundaries: never "in window"
+            const uint32_t l = (jj % G::W) / K, k = jj % K;
+            const uint32_t r = ii & (PANEL_H - 1);
+            const bool inwin = ((ii >> PANEL_H_LOG2) == wp) & ((jj / G::W) == ws) & ((r - wr0) <= (wr1 - wr0));
             const uint32_t t = r + l;
             const uint32_t bitpos = (t % SPC) * 2 * K + 2 * k;
-            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win + (t / SPC - wc0) * 32 + l);
-            return (w32[bitpos >> 5] >> (bitpos & 31u)) & 3u;
+            const uint32_t widx = inwin ? (((t / SPC - wc0) * 32 + l) * 4 + (bitpos >> 5)) : 0u;
+            const uint32_t word = reinterpret_cast<const uint32_t *>(win)[widx];
+            uint32_t code = inwin ? ((word >> (bitpos & 31u)) & 3u) : 7u;
+            code = (cj == 0u) ? bnd_col0 : code;                  // column 0: only delete_score is finite; local stops
+            code = (ci == 0u) ? ((cj == 0u) ? 0u : bnd_row0) : code;   // row 0; origin: sub_score == max == 0 (algo.rs:195-202)
+            return code;
         };
 
         unsigned long long dbg_iters = 0, dbg_reloads = 0;
@@ -124,9 +127,10 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             nops = 1;
             n_match = 1;
         } else {
+            uint32_t c0 = cell_code(i, j);
+            uint32_t end_i = i, end_j = j;
             for (;;) {
                 dbg_iters++;
-                uint32_t c0 = cell_code(i, j);
                 if (c0 == 7u) {
                     dbg_reloads++;
                     const long long dbg_r0 = P.debug ? clock64() : 0;
@@ -163,44 +167,49 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
                 // every lane looks x steps ahead in the direction of c0; the run ends at the first different code
                 const uint32_t x = (uint32_t)lane;
+                const bool diag = (c0 == 0u);
                 const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
-                const bool reach = (x * di <= i) && (x * dj <= j);
+                const bool reach = (x * di <= i) & (x * dj <= j);
                 const uint32_t ci = i - (reach ? x * di : 0u), cj = j - (reach ? x * dj : 0u);
-                uint32_t cx = reach ? cell_code(ci, cj) : 7u;
-                if (x > 0 && ci == 0 && cj == 0) cx = 7u;  // (0,0) is never emitted after a move (algo.rs:419-421)
+                uint32_t cx = cell_code(ci, cj);
+                cx = (!reach || (x > 0 && ci == 0 && cj == 0)) ? 7u : cx;   // (0,0) is never emitted after a move (algo.rs:419-421)
                 const uint32_t same = __ballot_sync(0xffffffffu, cx == c0);
                 const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
+                // the cell the walk reaches next is the one lane `run` just looked at: its code starts the next iteration
+                const uint32_t c_next = __shfl_sync(0xffffffffu, cx, (int)(run & 31u));
                 const bool mine = x < run;
-                if (c0 == 0u) {
-                    // is_match(i, j): Option<u8> equality, None == None (sequence.rs:113-114).  Run cells lie in the window,
-                    // so their label characters are in s1w / s2w.
-                    const int a = (mine && ci < m) ? (int)s1w[ci - s1w0] : -1;
-                    const int b = (mine && cj < n) ? (int)s2w[cj - s2w0] : -1;
-                    const uint32_t op = (a == b) ? 0u : 1u;
-                    const uint32_t mmask = __ballot_sync(0xffffffffu, mine && op == 0u);
-                    n_match += (uint32_t)__popc(mmask);
-                    n_mis += run - (uint32_t)__popc(mmask);
-                    if (mine) ops[nops + x] = (uint8_t)op;
-                    last = 0u;
-                } else {
-                    const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
-                    const bool opens = (last != ext);                  // algo.rs:373-379, 388-394
-                    const uint32_t op = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
-                    n_open += opens ? 1u : 0u;
-                    n_ext += opens ? run - 1u : run;
-                    last = ext;
-                    if (mine) ops[nops + x] = (uint8_t)op;
-                }
+                // labels.  Diagonal: is_match(i, j), Option<u8> equality with None == None (sequence.rs:113-114); run cells lie in
+                // the window, so their characters are in s1w / s2w.  Gaps: open/extend from last_choice (algo.rs:373-379, 388-394).
+                const bool lab = diag & mine;
+                const int a = (lab && ci < m) ? (int)s1w[ci - s1w0] : -1;
+                const int b = (lab && cj < n) ? (int)s2w[cj - s2w0] : -1;
+                const uint32_t mmask = __ballot_sync(0xffffffffu, lab && a == b);
+                const uint32_t nm = (uint32_t)__popc(mmask);
+                const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
+                const bool opens = !diag && (last != ext);
+                const uint32_t gop = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
+                const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
+                if (mine) ops[nops + x] = (uint8_t)op;
+                n_match += nm;
+                n_mis += diag ? run - nm : 0u;
+                n_open += opens ? 1u : 0u;
+                n_ext += diag ? 0u : (opens ? run - 1u : run);
+                last = diag ? 0u : ext;
                 nops += run;
                 // last emitted cell, then the checked_sub move (algo.rs:412-417); run cells are all inside the table
-                res.end_i = i - (run - 1u) * di;
-                res.end_j = j - (run - 1u) * dj;
+                end_i = i - (run - 1u) * di;
+                end_j = j - (run - 1u) * dj;
                 const bool i_none = di && (i < run), j_none = dj && (j < run);
                 if (i_none && j_none) break;
                 i = i_none ? 0u : i - run * di;
                 j = j_none ? 0u : j - run * dj;
                 if (i == 0 && j == 0) break;
+                // lane `run` looked at exactly (i, j) unless the run used all 32 lanes, the move was clamped, or that
+                // cell was outside the window (7): then look it up (and reload the window at the top of the loop)
+                c0 = (run < 32u && !i_none && !j_none && c_next != 7u) ? c_next : cell_code(i, j);
             }
+            res.end_i = end_i;
+            res.end_j = end_j;
         }
         if (P.debug) {
             res.lcs_at_first_max = dbg_iters | (dbg_reloads << 32);
