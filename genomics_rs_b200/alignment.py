@@ -49,6 +49,7 @@ class AlignedSequences:
     end: Tuple[int, int] = (0, 0)
     fill_ms: float = 0.0
     walk_ms: float = 0.0
+    matches_at_max: Optional[int] = None           # alignment_table's 2nd return value (algo.rs:279-281), on request
     _ij: Optional[Tuple[np.ndarray, np.ndarray]] = field(default=None, repr=False)
 
     def coords(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -97,7 +98,7 @@ class Plan:
     """gx_plan wrapper: geometry fixed at creation, sequences uploaded once, executed any number of times."""
 
     def __init__(self, len1, len2, scores, is_local: bool, traceback: bool = True, start_cell: bool = False,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, lcs_at_max: bool = False):
         self.lib = _lib.ensure_init(device)
         self.len1 = np.ascontiguousarray(len1, np.uint64)
         self.len2 = np.ascontiguousarray(len2, np.uint64)
@@ -105,7 +106,8 @@ class Plan:
         self.n_pairs = int(self.len1.size)
         self.traceback = bool(traceback)
         self.is_local = bool(is_local)
-        flags = (_lib.GX_FLAG_TRACEBACK if traceback else 0) | (_lib.GX_FLAG_START_CELL if start_cell else 0)
+        flags = ((_lib.GX_FLAG_TRACEBACK if traceback else 0) | (_lib.GX_FLAG_START_CELL if start_cell else 0) |
+                 (_lib.GX_FLAG_LCS_AT_MAX if lcs_at_max else 0))
         self._h = C.c_void_p()
         _lib.check(self.lib.gx_plan_create(self.len1.ctypes.data, self.len2.ctypes.data, self.n_pairs,
                                            _scores_struct(scores), int(self.is_local), flags, C.byref(self._h)))
@@ -190,10 +192,10 @@ class DeviceTable:
 
 
 def alignment_table(sequence_container: SequenceContainer, scores, is_local: bool,
-                    reverse_sequences: bool = False) -> Tuple[DeviceTable, Optional[int]]:
+                    reverse_sequences: bool = False, matches_at_max: bool = False) -> Tuple[DeviceTable, Optional[int]]:
     """algo.rs:151-282.  Fills S/D/I on the GPU (and the direction codes retrace needs).
-    The second return value (LCS length at the first max cell, algo.rs:279-281) is discarded by every
-    caller of the reference and is not computed: None."""
+    The second return value (max_matches at the first max cell, algo.rs:279-281) is discarded by every caller of
+    the reference; it costs a second fill pass, so it is computed only with matches_at_max=True (else None)."""
     if reverse_sequences:
         raise NotImplementedError("reverse_sequences is never passed by the reference (dead code, sequence.rs:103-112)")
     if len(sequence_container.sequences) > 2:                     # algo.rs:161-163
@@ -201,13 +203,17 @@ def alignment_table(sequence_container: SequenceContainer, scores, is_local: boo
     s1 = sequence_container.sequences[0]                           # IndexError <-> index panic, algo.rs:168-169
     s2 = sequence_container.sequences[1]
     b1, b2 = _as_u8(s1.sequence), _as_u8(s2.sequence)
-    plan = Plan([b1.size], [b2.size], scores, is_local, traceback=True)
+    plan = Plan([b1.size], [b2.size], scores, is_local, traceback=True, lcs_at_max=matches_at_max)
     blob = np.concatenate([b1, b2]) if (b1.size + b2.size) else np.zeros(0, np.uint8)
     plan.upload(blob, [0], [b1.size])
     plan.execute()
     log.info("Sequence table shape: [%d, %d]", b1.size + 1, b2.size + 1)
     log.info("Table initialization complete, time taken: %dus", int(plan.fill_ms * 1000))
-    return DeviceTable(plan, s1, s2, is_local), None
+    second = None
+    if matches_at_max:
+        res, _, _ = plan.fetch()
+        second = int(res[0]["lcs_at_first_max"])
+    return DeviceTable(plan, s1, s2, is_local), second
 
 
 def retrace(sequence_container: SequenceContainer, alignment_table_: DeviceTable, is_local: bool) -> AlignedSequences:
@@ -252,7 +258,8 @@ def pack_pairs(pairs: Seq[Tuple[object, object]]):
 
 
 def align_batch(pairs: Seq[Tuple[object, object]], scores, is_local: bool, traceback: bool = True,
-                start_cell: bool = False, names: Optional[Seq[Tuple[str, str]]] = None) -> List[AlignedSequences]:
+                start_cell: bool = False, names: Optional[Seq[Tuple[str, str]]] = None,
+                lcs_at_max: bool = False) -> List[AlignedSequences]:
     """Many independent pairs in one gx_align_batch call (one GPU; shard over ranks with parallel.scatter)."""
     lib = _lib.ensure_init()
     blob, off1, len1, off2, len2 = pack_pairs(pairs)
@@ -261,7 +268,8 @@ def align_batch(pairs: Seq[Tuple[object, object]], scores, is_local: bool, trace
     ops_off = np.zeros(n + 1, np.uint64)
     np.cumsum(len1 + len2 + np.uint64(1), out=ops_off[1:])
     ops = np.zeros(int(ops_off[-1]) if traceback else 0, np.uint8)
-    flags = (_lib.GX_FLAG_TRACEBACK if traceback else 0) | (_lib.GX_FLAG_START_CELL if start_cell else 0)
+    flags = ((_lib.GX_FLAG_TRACEBACK if traceback else 0) | (_lib.GX_FLAG_START_CELL if start_cell else 0) |
+             (_lib.GX_FLAG_LCS_AT_MAX if lcs_at_max else 0))
     _lib.check(lib.gx_align_batch(blob.ctypes.data if blob.size else None, blob.size, off1.ctypes.data, len1.ctypes.data,
                                   off2.ctypes.data, len2.ctypes.data, n, _scores_struct(scores), int(bool(is_local)), flags,
                                   res.ctypes.data, ops.ctypes.data if traceback else None, ops_off.ctypes.data))
@@ -279,7 +287,8 @@ def align_batch(pairs: Seq[Tuple[object, object]], scores, is_local: bool, trace
             mismatches=int(r["mismatches"]), gap_extensions=int(r["gap_extensions"]), opening_gaps=int(r["opening_gaps"]),
             ops=ops[o:o + k].copy() if traceback else np.zeros(0, np.uint8),
             start=(int(r["start_i"]), int(r["start_j"])), end=(int(r["end_i"]), int(r["end_j"])),
-            fill_ms=float(r["fill_ms"]), walk_ms=float(r["walk_ms"])))
+            fill_ms=float(r["fill_ms"]), walk_ms=float(r["walk_ms"]),
+            matches_at_max=int(r["lcs_at_first_max"]) if lcs_at_max else None))
     return out
 
 

@@ -11,6 +11,7 @@
 
 #include "../../include/gxalign.h"
 #include "gx_fill.cuh"
+#include "gx_lcs.cuh"
 #include "gx_reads.cuh"
 #include "gx_walk.cuh"
 
@@ -149,6 +150,12 @@ struct gx_plan {
     int2 *d_top = nullptr;
     uint8_t *d_codes = nullptr;
     int4 *d_best = nullptr;
+    // GX_FLAG_LCS_AT_MAX: first-maximum pass + bit-vector LCS (gx_lcs.cuh)
+    bool lcs = false;
+    int4 *d_first = nullptr;
+    uint32_t *d_masks = nullptr, *d_carry = nullptr;
+    uint32_t carry_words = 0;
+    float lcs_ms = 0;
     gx::DevResult *d_results = nullptr;
     uint8_t *d_ops = nullptr;
     // reads kind
@@ -197,11 +204,12 @@ static FillKernel pick_fill(bool prof, bool chain1, bool L, bool C, int track) {
 }
 
 template <int K>
-static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap) {
+static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int track_override = -1) {
     Ctx *c = pl->ctx;
     void (*kern)(const FillParams) = nullptr;
     const bool L = pl->is_local != 0, C = pl->traceback;
-    kern = pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
+    kern = (track_override >= 0) ? pick_fill<K>(pl->prof, pl->chain1, L, false, track_override)
+                                 : pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
     // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
     int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * WARPS_PER_SM) ? WARPS_PER_CTA : 1;
     if (const char *e = getenv("GX_WPC")) wpc = atoi(e) == 1 ? 1 : WARPS_PER_CTA;
@@ -244,7 +252,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best,
+    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best, pl->d_first, pl->d_masks, pl->d_carry,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -379,7 +387,6 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     *out = nullptr;
     if (!g_ctx) return GX_ERR_NOT_INIT;
     if ((!len1 || !len2) && n_pairs) return GX_ERR_ARG;
-    if (flags & GX_FLAG_LCS_AT_MAX) return GX_ERR_UNSUPPORTED;
     if (n_pairs >= (1ull << 31)) return GX_ERR_RANGE;
     Ctx *c = g_ctx;
     CK(cudaSetDevice(c->device));
@@ -408,7 +415,16 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     for (uint64_t q = 0; q < n_pairs; ++q) pl->cells += (len1[q] + 1) * (len2[q] + 1);
 
     // short-read batches without traceback go to the inter-task kernel (K4)
-    const bool reads = !band_col0 && !pl->traceback && pl->track != 2 && n_pairs >= 1024 && max_len <= (uint64_t)READS_MAX_LEN &&
+    pl->lcs = (flags & GX_FLAG_LCS_AT_MAX) != 0 && !band_col0;
+    if (pl->lcs) {
+        // the first-maximum keys are (V << log2 K) | k in int32 for every cell, global mode included
+        long long mx = std::max({std::llabs((long long)sc.s_match), std::llabs((long long)sc.s_mismatch), std::llabs((long long)sc.g)});
+        if (n_pairs > 65536 || (long long)(2 * max_len + 2) * mx + std::llabs((long long)sc.h) >= (1ll << 26)) {
+            delete pl;
+            return n_pairs > 65536 ? GX_ERR_UNSUPPORTED : GX_ERR_RANGE;
+        }
+    }
+    const bool reads = !pl->lcs && !band_col0 && !pl->traceback && pl->track != 2 && n_pairs >= 1024 && max_len <= (uint64_t)READS_MAX_LEN &&
                        (!is_local || sc.s_mismatch < 0);
     pl->kind = reads ? KIND_READS : KIND_WAVEFRONT;
     int rc = GX_OK;
@@ -542,6 +558,12 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     A(top * 8, (void **)&pl->d_top);
     if (pl->traceback) A(codes, (void **)&pl->d_codes);
     if (pl->is_local) A(best * 16, (void **)&pl->d_best);
+    if (pl->lcs) {
+        pl->carry_words = (uint32_t)((max_len + 31) / 32 + 1);
+        A(best * 16 + 16, (void **)&pl->d_first);
+        A((size_t)n_pairs * 256 * LCS_BLOCK_WORDS * 4, (void **)&pl->d_masks);
+        A((size_t)n_pairs * 2 * pl->carry_words * 4 + 16, (void **)&pl->d_carry);
+    }
     A(n_pairs * sizeof(DevResult), (void **)&pl->d_results);
     if (pl->traceback) A(ops, (void **)&pl->d_ops);
     if (rc == GX_OK && !tiles.empty()) {
@@ -911,9 +933,40 @@ int gx_plan_execute(gx_plan *pl) {
     CK(cudaEventRecord(c->ev[2], c->stream));
     uint32_t abort_word = 0;
     CK(cudaMemcpyAsync(&abort_word, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t abort_word2 = 0;
+    if (pl->lcs) {
+        // alignment_table's second return value: a score-only fill pass that tracks the FIRST maximum, then the LCS
+        // length of the two prefixes that end there (gx_lcs.cuh)
+        if (pl->n_tiles) {
+            CK(cudaMemsetAsync(pl->d_ctrl, 0, (16 + pl->progress_entries) * 4, c->stream));
+            FillParams fq = fp;
+            fq.parity = pl->parity ^ 1u;
+            fq.codes = nullptr;
+            fq.tile_best = pl->d_first;
+            fq.stats = nullptr;
+            fq.timeline = nullptr;
+            int rc = pl->K == 16 ? launch_fill<16>(pl, fq, 0, 3) : pl->K == 4 ? launch_fill<4>(pl, fq, 0, 3) : launch_fill<8>(pl, fq, 0, 3);
+            if (rc) return rc;
+            pl->launches++;
+            CK(cudaMemcpyAsync(&abort_word2, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        LcsParams lp;
+        lp.blob = pl->d_blob;
+        lp.pairs = pl->d_pairs;
+        lp.n_pairs = (uint32_t)pl->n_pairs;
+        lp.tile_first = pl->d_first;
+        lp.masks = pl->d_masks;
+        lp.carry = pl->d_carry;
+        lp.carry_words = pl->carry_words;
+        lp.results = pl->d_results;
+        gx_lcs_kernel<<<(unsigned)pl->n_pairs, 32, 0, c->stream>>>(lp);
+        CK(cudaGetLastError());
+        pl->launches++;
+        CK(cudaEventRecord(c->ev[3], c->stream));
+    }
     if (fp.stats) CK(cudaMemcpyAsync(pl->h_stats, pl->d_stats, 64, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (abort_word) {
+    if (abort_word || abort_word2) {
         g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";
         if (bd && bd->n_bands > bd->last - bd->first) bd->poisoned = true;
         return GX_ERR_INTERNAL;
@@ -921,7 +974,8 @@ int gx_plan_execute(gx_plan *pl) {
     if (bd) bd->epoch++;
     CK(cudaEventElapsedTime(&pl->fill_ms, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&pl->walk_ms, c->ev[1], c->ev[2]));
-    pl->parity ^= 1u;
+    if (pl->lcs) CK(cudaEventElapsedTime(&pl->lcs_ms, c->ev[2], c->ev[3]));
+    if (!(pl->lcs && pl->n_tiles)) pl->parity ^= 1u;   // with the first-maximum pass the fill ran twice: parity is back
     pl->colbuf_dirty = false;
     pl->executed = true;
     return GX_OK;
@@ -1023,6 +1077,7 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 9: return (double)pl->kind;
         case 15: return (double)pl->K;
         case 17: return pl->chain1 ? 1.0 : 0.0;
+        case 18: return pl->lcs_ms;
         case 10: case 11: case 12: case 13: case 14: return (double)pl->h_stats[what - 10];
         default: return -1.0;
     }

@@ -165,7 +165,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                 for (int k = 0; k < K; ++k) sub[k] = (c1 == c2[k]) ? ap : bp;
             }
             int e = el, irun = il, ed = vd;
-            int rowbest = CHAIN1 ? INT32_MIN : -1;
+            int rowbest = (CHAIN1 || TRACK == 3) ? INT32_MIN : -1;
             int mh = el;   // CHAIN1: "max(D,S) of the cell to the left" -- for the lane's first column that is E_left itself
             static_for<K>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
@@ -218,6 +218,12 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                     int key = Vkey;
                     if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
                     rowbest = max(rowbest, key);
+                } else if (TRACK == 3) {
+                    // first maximum in row-major order (alignment_table's max_cell, algo.rs:258-262, strict `<`):
+                    // inside the row the key's low bits prefer the SMALLER column
+                    int key = (Vkey << KB) | (K - 1 - k);
+                    if (PAD) key = (k < kvalid) ? key : INT32_MIN;
+                    rowbest = max(rowbest, key);
                 }
             });
             if (MASKED) vd = active ? el : vd;
@@ -232,6 +238,11 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                 best_r = upd ? r : best_r;
             } else if (TRACK == 1) {
                 best = active ? max(best, rowbest) : best;
+            } else if (TRACK == 3) {
+                // only a strictly larger value replaces the running first maximum (rows arrive in increasing order)
+                const bool upd = active && ((rowbest | (K - 1)) > (best | (K - 1)));
+                best = upd ? rowbest : best;
+                best_r = upd ? r : best_r;
             }
             if (lane == 31 && active) outring[step] = make_uint2((uint32_t)e, (uint32_t)irun);   // row t0+step-31
         });
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
         if (dead) break;
 
         int elast = 0, ilast = 0;
-        int best = CHAIN1 ? INT32_MIN : -1, best_r = 0;
+        int best = (CHAIN1 || TRACK == 3) ? INT32_MIN : -1, best_r = 0;
         const uint32_t nbat = tile_batches((uint32_t)rows, B);
         uint4 *code_base = nullptr;
         if (CODES)
@@ -607,6 +618,10 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
                 else bv = (best < 0) ? -1 : (best >> KB);
                 bi = i0 + best_r + 1;
                 bj = jl + (best & (K - 1)) + 1;
+            } else if (TRACK == 3) {
+                bv = (kvalid == 0) ? INT32_MIN : (best >> KB) - (CHAIN1 ? hg : 0);
+                bi = i0 + best_r + 1;
+                bj = jl + (K - 1 - (best & (K - 1))) + 1;
             } else {
                 if (CHAIN1) bv = (kvalid == 0) ? -1 : best - hg;
                 else bv = best;
@@ -618,7 +633,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const
                 const int ov = __shfl_xor_sync(FULL, bv, off);
                 const int oi = __shfl_xor_sync(FULL, bi, off);
                 const int oj = __shfl_xor_sync(FULL, bj, off);
-                const bool take = (ov > bv) || (ov == bv && (oi > bi || (oi == bi && oj > bj)));
+                const bool take = (TRACK == 3) ? ((ov > bv) || (ov == bv && (oi < bi || (oi == bi && oj < bj))))
+                                               : ((ov > bv) || (ov == bv && (oi > bi || (oi == bi && oj > bj))));
                 bv = take ? ov : bv;
                 bi = take ? oi : bi;
                 bj = take ? oj : bj;

@@ -31,6 +31,7 @@ pub struct gx_result {
 
 pub const GX_OK: c_int = 0;
 pub const GX_FLAG_TRACEBACK: c_int = 1;
+pub const GX_FLAG_LCS_AT_MAX: c_int = 2; // gx_result.lcs_at_first_max = alignment_table's 2nd return value
 pub const GX_BAND_HANDLE_BYTES: usize = 64;
 
 /// opaque: this process's column bands of one wide global table (include/gxalign.h, gx_band_*)

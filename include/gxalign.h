@@ -59,7 +59,7 @@ enum {
 /* ---- flags */
 enum {
     GX_FLAG_TRACEBACK = 1,    /* fill direction codes and walk them (retrace, algo.rs:287-441) */
-    GX_FLAG_LCS_AT_MAX = 2,   /* also return alignment_table's 2nd value (algo.rs:279-281) -- not implemented yet */
+    GX_FLAG_LCS_AT_MAX = 2,   /* also return alignment_table's 2nd value (algo.rs:279-281): max_matches at the first max cell */
     GX_FLAG_START_CELL = 4    /* score-only local: also report the start cell (last argmax, algo.rs:311-322) */
 };
 
@@ -125,7 +125,8 @@ int gx_plan_fetch_scores(gx_plan *plan, int64_t *scores);   /* scores only: 4 B 
 void gx_plan_destroy(gx_plan *plan);
 /* introspection for benchmarks: what==0 fill ms, 1 walk ms, 2 kernels launched by the last execute,
  * 3 cells (sum (m+1)(n+1)), 4 traceback bytes written per execute, 5 device bytes held by the plan,
- * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch) */
+ * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch),
+ * 15 K, 17 recurrence form (1 = CHAIN1), 18 ms of the GX_FLAG_LCS_AT_MAX passes */
 double gx_plan_stat(const gx_plan *plan, int what);
 /* debug (GX_FILL_STATS=2): per tile {ticket ns, first DP step ns, end ns, pair<<48|panel<<32|strip<<12|sm}; cap_words >= 4 * tiles */
 int gx_plan_debug_timeline(gx_plan *plan, uint64_t *out, uint64_t cap_words);

@@ -186,6 +186,47 @@ def test_corona_all_vs_all(gx, oracle, goldens):
         assert "%016x" % oracle.hash_ops(r.ops, r.start) == g["op_hash"], (a, b)
 
 
+def test_matches_at_max(gx, oracle, goldens):
+    """alignment_table's second return value (algo.rs:279-281): max_matches (the LCS-length lanes, algo.rs:112-121,
+    250-255) at the FIRST cell attaining the table maximum (algo.rs:258-262) -- against the faithful oracle on random
+    pairs (ties are frequent in small tables) and against the goldens of every fixture, global and local"""
+    for scores in (CONFIG_TOML, TEST_CONFIG, (2, -1, -1, 0)):
+        rng = np.random.default_rng(31 + scores[0])
+        pairs = [random_pair(rng, int(rng.integers(0, 90)), int(rng.integers(0, 90)), alphabet=b"ACGT" if k % 3 else b"AC",
+                             similar=bool(k % 2)) for k in range(150)]
+        pairs += [random_pair(rng, m, n) for m, n in ((700, 900), (4100, 300), (300, 4200), (2500, 2600))]
+        pairs += [(b"\x00\xff\x80ABCDEFG" * 9, b"\xffA\x80CDXFG\x00" * 11)]
+        for is_local in (False, True):
+            got = gx.align_batch(pairs, scores, is_local, lcs_at_max=True)
+            for (a, b), r in zip(pairs, got):
+                o = oracle.align_faithful(a, b, scores, is_local)
+                assert r.matches_at_max == o.lcs_at_first_max, (len(a), len(b), scores, is_local, o.first_max)
+                assert r.score == o.score and np.array_equal(r.ops, o.ops)      # the extra passes leave the alignment alone
+    for fixture in ("test1", "test2_short", "test3_short", "test4", "Opsin1_colorblindness_gene", "Human-Mouse-BRCA2-cds"):
+        s = read_fasta_gz(fixture)
+        for is_local in (False, True):
+            g = next(p for p in goldens["pairs"] if p["fixture"] == fixture and p["is_local"] == is_local)
+            sc = gx.SequenceContainer(sequences=[gx.Sequence(*s[0]), gx.Sequence(*s[1])])
+            table, second = gx.alignment_table(sc, gx.Scores(*CONFIG_TOML), is_local, False, matches_at_max=True)
+            assert second == g["lcs_at_first_max"], (fixture, is_local)
+            assert gx.retrace(sc, table, is_local).score == g["score"]
+    # tables wider than one 32768-column block of the bit-vector pass: the local maximum sits behind column 40000
+    rng = np.random.default_rng(77)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    a = lut[rng.integers(0, 4, size=3000)]
+    core = a.copy()
+    idx = rng.choice(3000, size=150, replace=False)
+    core[idx] = lut[rng.integers(0, 4, size=150)]
+    b = np.concatenate([lut[rng.integers(0, 4, size=40000)], core[:1400], core[1430:], lut[rng.integers(0, 4, size=27000)]])
+    for is_local in (True, False):
+        r = gx.align_batch([(a, b)], CONFIG_TOML, is_local, traceback=False, lcs_at_max=True)[0]
+        o = oracle.align_linear(a, b, CONFIG_TOML, is_local, traceback=False)
+        assert r.score == o.score
+        assert r.matches_at_max == o.lcs_at_first_max, (is_local, o.first_max, o.lcs_at_first_max)
+        if is_local:
+            assert o.first_max[1] > 32768
+
+
 def test_read_batch_scores(gx, oracle):
     """BASELINE config 4 shape: many 150 bp pairs, local score only (inter-task kernel), plus ragged lengths."""
     rng = np.random.default_rng(150)
