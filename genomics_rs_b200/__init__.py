@@ -3,12 +3,12 @@ nlaha/genomics-rs (src/alignment/algo.rs).  The product is libgxalign.so (CUDA +
 this package is the host-side mirror of the reference's interface around it.  No CPU fallback."""
 from .config import Config, Scores, get_config, parse_config
 from .sequence import Sequence, SequenceContainer
-from .alignment import (AlignedSequences, AlignmentChoice, DeviceTable, Plan, RESULT_DTYPE, align, align_batch,
+from .alignment import (AlignedSequences, AlignmentChoice, DeviceTable, Plan, RESULT_DTYPE, align, align_all, align_batch,
                         alignment_table, k0_measure, pack_pairs, retrace, score_batch)
 from .banded import Band, band_range, nw_score_banded, nw_score_banded_local
 from . import _lib
 
 __all__ = ["Config", "Scores", "get_config", "parse_config", "Sequence", "SequenceContainer", "AlignedSequences",
-           "AlignmentChoice", "DeviceTable", "Plan", "RESULT_DTYPE", "align", "align_batch", "alignment_table",
+           "AlignmentChoice", "DeviceTable", "Plan", "RESULT_DTYPE", "align", "align_all", "align_batch", "alignment_table",
            "k0_measure", "pack_pairs", "retrace", "score_batch",
            "Band", "band_range", "nw_score_banded", "nw_score_banded_local"]

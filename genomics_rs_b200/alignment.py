@@ -292,6 +292,16 @@ def align_batch(pairs: Seq[Tuple[object, object]], scores, is_local: bool, trace
     return out
 
 
+def align_all(sequence_container: SequenceContainer, scores, is_local: bool, traceback: bool = True):
+    """All-vs-all over a container (BASELINE config 3 as a product feature): every pair (a, b), a < b,
+    s1 = sequences[a], in one gx_align_batch call.  -> [((a, b), AlignedSequences)]"""
+    seqs = sequence_container.sequences
+    jobs = [(a, b) for a in range(len(seqs)) for b in range(a + 1, len(seqs))]
+    out = align_batch([(seqs[a].sequence, seqs[b].sequence) for a, b in jobs], scores, is_local, traceback=traceback,
+                      names=[(seqs[a].name, seqs[b].name) for a, b in jobs])
+    return list(zip(jobs, out))
+
+
 def score_batch(blob: np.ndarray, off1, len1, off2, len2, scores, is_local: bool, out: Optional[np.ndarray] = None) -> np.ndarray:
     """gx_score_batch: scores only (int64), the short-read workload's entry point.
     `out` (int64, one entry per pair) may be supplied to keep the result buffer across calls."""

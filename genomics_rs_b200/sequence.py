@@ -64,6 +64,15 @@ class SequenceContainer:
         log.debug("Loaded %d sequences", len(sequences))
         self.sequences.extend(sequences)
 
+    def from_fasta_dir(self, fasta_dir: str) -> None:
+        """Directory ingestion of the reference's `compare` sub-command (main.rs:227-239): every file whose extension is
+        `fasta`, all of its records.  Files are taken in SORTED name order: read_dir order is unspecified and NW with the
+        reference's tie-breaks is not symmetric, so the order is part of the contract."""
+        import os
+        for name in sorted(os.listdir(fasta_dir)):
+            if name.rsplit(".", 1)[-1] == "fasta" and "." in name:
+                self.from_fasta(os.path.join(fasta_dir, name))
+
     def is_match(self, i: int, j: int, reverse_sequences: bool = False) -> bool:
         """sequence.rs:102-115.  Option<u8> equality: both out of range compares equal (None == None)."""
         s1 = self.sequences[0].bytes()

@@ -227,6 +227,33 @@ def test_matches_at_max(gx, oracle, goldens):
             assert o.first_max[1] > 32768
 
 
+def test_align_all_directory(gx, goldens, tmp_path):
+    """directory ingestion + all-vs-all through one batch call, Python mirror and the C++ CLI"""
+    import gzip, os, subprocess
+    order = goldens["corona_order"][:3]
+    for name in order:
+        raw = gzip.open(os.path.join(os.path.dirname(__file__), "golden", "fasta", name + ".fasta.gz"), "rb").read()
+        (tmp_path / (name + ".fasta")).write_bytes(raw)
+    sc = gx.SequenceContainer()
+    sc.from_fasta_dir(str(tmp_path))
+    assert len(sc.sequences) == 3
+    gold = {tuple(c["pair"]): c for c in goldens["corona"]}
+    res = gx.align_all(sc, gx.Scores(*CONFIG_TOML), False)
+    assert [j for j, _ in res] == [(0, 1), (0, 2), (1, 2)]
+    for (a, b), r in res:
+        g = gold[(a, b)]
+        assert r.score == g["score"] and len(r.ops) == g["n_ops"] and r.matches == g["matches"]
+    cli = os.path.join(os.path.dirname(os.path.dirname(__file__)), "genomics_rs_b200", "host", "gxalign_cli")
+    if os.path.exists(cli):
+        cfg = tmp_path / "config.toml"
+        cfg.write_text("[scores]\ns_match = 1\ns_mismatch = -2\ng = -1\nh = -5\n")
+        out = subprocess.run([cli, "--config-path", str(cfg), "align-all", "-a", "global", "--fasta-dir", str(tmp_path)],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        rows = [ln.split("\t") for ln in out.stdout.splitlines() if ln and not ln.startswith("#")][1:]
+        assert [int(r[2]) for r in rows] == [gold[p]["score"] for p in ((0, 1), (0, 2), (1, 2))]
+
+
 def test_read_batch_scores(gx, oracle):
     """BASELINE config 4 shape: many 150 bp pairs, local score only (inter-task kernel), plus ragged lengths."""
     rng = np.random.default_rng(150)

@@ -117,3 +117,14 @@ def test_display_matches_reference_format():
     assert t.endswith("Percent Identity 100%\n")
     c = _aligned("ACG", "ACG", [0, 0, 1], 0, (2, 1, 0, 0))
     assert "Percent Identity 66.66666666666666%\n" in str(c)
+
+
+def test_fasta_dir_ingestion(tmp_path):
+    """main.rs:227-239: every *.fasta file, all of its records; sorted file-name order is our contract"""
+    (tmp_path / "b.fasta").write_text(">b1\nACGT\n>b2\nAC\n")
+    (tmp_path / "a.fasta").write_text(">a\nGG\nTT\n")
+    (tmp_path / "c.txt").write_text(">x\nAA\n")
+    (tmp_path / "fasta").write_text(">y\nAA\n")          # no extension: skipped like Path::extension() == None
+    sc = gx.SequenceContainer()
+    sc.from_fasta_dir(str(tmp_path))
+    assert [(s.name, s.sequence) for s in sc.sequences] == [("a", "GGTT"), ("b1", "ACGT"), ("b2", "AC")]
