@@ -32,6 +32,19 @@ SCORES = wl.CONFIG_TOML
 OPS_PER_CELL = {"global_score": 7, "local_score": 8, "traceback": 13}
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed ncu capture of the same command
+    (profiles/r1d_traffic.json, written from `ncu --set full`); None when no capture exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "r1d_traffic.json")
+    key = {"corona45": "prof_fill_corona45"}.get(workload)
+    if key is None or not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(key)
+    if not d:
+        return None, None
+    return d["dram_read_bytes"] + d["dram_write_bytes"], "profiles/r1d_traffic.json (ncu --set full, one launch of the fill kernel)"
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -332,6 +345,10 @@ def main():
                 "peak_basis": f"{sms} SMs x {lanes:.0f} INT32 lanes/clk x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                 "gcups_kernel": my_cells / (fill_ms / args.steps * 1e-3) / 1e9,
                 "traffic": None}
+        if world == 1:
+            roof["traffic"], roof["traffic_source"] = ncu_traffic(args.workload)
+            if w["traceback"]:
+                roof["algorithmic_bytes"] = float(plan.stat(4))     # 2-bit codes written once per cell
         hbm = None
         if w["traceback"]:
             gbs = float(plan.stat(4)) / (fill_ms / args.steps * 1e-3) / 1e9
