@@ -232,7 +232,9 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
 
 template <int K>
 static int launch_walk(gx_plan *pl, const WalkParams &wp) {
-    gx_walk_kernel<K><<<(unsigned)pl->n_pairs, 32, 0, pl->ctx->stream>>>(wp);
+    const uint32_t smem = wp.traceback ? walk_smem_bytes(K) : 0u;
+    CK(cudaFuncSetAttribute(gx_walk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(K)));
+    gx_walk_kernel<K><<<(unsigned)pl->n_pairs, 32, smem, pl->ctx->stream>>>(wp);
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -470,7 +472,9 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
                 strips16 += (len2[q] + 511) / 512;
                 strips8 += (len2[q] + 255) / 256;
             }
-        pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 2 >= resident || max_len < 2048) ? 8 : 4);
+        // measured on corona shards (tools/timeline_wl.py): 45 pairs K=16 ~ K=8; 23 pairs K=8 ~ K=4 << K=16;
+        // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
+        pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
         if (const char *e = getenv("GX_K")) {
             const int k = atoi(e);
             if (k == 4 || k == 8 || k == 16) pl->K = k;

@@ -19,6 +19,12 @@
 
 namespace gx {
 
+// dynamic shared memory of one walk warp: two window buffers (codes + label characters)
+__host__ __device__ constexpr uint32_t walk_buf_bytes(int K) {
+    return (uint32_t)(((256 + 32 + 64 / K - 1) / (64 / K) + 1) * 32 * 16 + (256 + 32) + (32 * K + 32) + 15) & ~15u;
+}
+__host__ __device__ constexpr uint32_t walk_smem_bytes(int K) { return 2 * walk_buf_bytes(K); }
+
 template <int K>
 __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     const uint32_t q = blockIdx.x;
@@ -88,12 +94,19 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
         constexpr int SPC = G::SPC;
         constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
         constexpr int NCH = (WR + 32 + SPC - 1) / SPC + 1;    // code chunks per fill-lane in a window
-        __shared__ uint4 win[NCH * 32];                       // [chunk][fill-lane]
-        // label characters of the window: is_match(i,j) reads s1[i] and s2[j] (0-based: the characters AFTER the
-        // cell's own, algo.rs:354), i.e. s1[i0w+1 .. ] for the window's rows and s2[j0w+1 .. ] for the strip's columns
-        __shared__ uint8_t s1w[WR + 32];
-        __shared__ uint8_t s2w[G::W + 32];
+        // Two window buffers in dynamic shared memory: the walk reads buffer `cb`; the other one receives the window the
+        // walk will probably need next (prefetched with cp.async while the walk runs).  Per buffer: code chunks
+        // [chunk][fill-lane] + the label characters of the window: is_match(i,j) reads s1[i] and s2[j] (0-based: the
+        // characters AFTER the cell's own, algo.rs:354), i.e. s1[i0w+1 ..] for the rows and s2[j0w+1 ..] for the columns.
+        extern __shared__ __align__(16) uint8_t walk_smem[];
+        constexpr uint32_t BUF_BYTES = walk_buf_bytes(K);
+        uint32_t cb = 0;
+        const uint4 *win = reinterpret_cast<const uint4 *>(walk_smem);
+        const uint8_t *s1w = walk_smem + NCH * 32 * 16;
+        const uint8_t *s2w = s1w + (WR + 32);
         uint32_t s1w0 = 0, s2w0 = 0;                          // sequence index of s1w[0] / s2w[0]
+        // prefetched window (in buffer cb ^ 1): tile (np, ns), local rows [nr0, nr1]; np = 0xffffffff: none
+        uint32_t np = 0xffffffffu, ns = 0, nr0 = 0, nr1 = 0;
         uint8_t *ops = P.ops + pd->ops_off;
         uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
         uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
@@ -134,34 +147,96 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 if (c0 == 7u) {
                     dbg_reloads++;
                     const long long dbg_r0 = P.debug ? clock64() : 0;
-                    // (re)load the window that ends at this row: rows [r-255, r] x all 32 fill-lanes of the tile
                     const uint32_t jj = j - 1, ii = i - 1;
-                    wp = ii >> PANEL_H_LOG2;
-                    ws = jj / G::W;
-                    wr1 = ii & (PANEL_H - 1);
-                    wr0 = (wr1 >= WR - 1) ? wr1 - (WR - 1) : 0;
-                    wc0 = wr0 / SPC;
-                    const uint32_t nch = (wr1 + 31) / SPC - wc0 + 1;   // <= NCH
-                    const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
-                                                                         (uint64_t)(wp * pd->S + ws) * pd->tile_code_bytes) +
-                                        (size_t)wc0 * 32 + lane;
-                    __syncwarp();
-                    {
-                        // asynchronous global -> shared copies: all chunks in flight at once, one memory latency per window
-                        uint32_t dst = smem_u32(win + lane);
-                        for (uint32_t b = 0; b < nch; ++b) {
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)b * 32) : "memory");
+                    const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
+                    // copies of `nch` chunks of tile (p, s) starting at chunk c0w into buffer b (asynchronous)
+                    auto issue_codes = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) {
+                        const uint32_t c0w = r0 / SPC;
+                        const uint32_t nch = (r1 + 31) / SPC - c0w + 1;   // <= NCH
+                        const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
+                                                                             (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
+                                            (size_t)c0w * 32 + lane;
+                        uint32_t dst = smem_u32(walk_smem + b * BUF_BYTES) + (uint32_t)lane * 16u;
+                        for (uint32_t q2 = 0; q2 < nch; ++q2) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)q2 * 32) : "memory");
                             dst += 32 * 16;
                         }
-                        // label characters: rows wr0..wr1 of panel wp -> s1 indices (i-1)+1, columns of strip ws -> s2 indices (j-1)+1
-                        s1w0 = (wp << PANEL_H_LOG2) + wr0 + 1u;
-                        s2w0 = ws * G::W + 1u;
-                        for (uint32_t k = (uint32_t)lane; k <= wr1 - wr0; k += 32) s1w[k] = (s1w0 + k < m) ? __ldg(s1 + s1w0 + k) : (uint8_t)0;
-                        for (uint32_t k = (uint32_t)lane; k < (uint32_t)G::W; k += 32) s2w[k] = (s2w0 + k < n) ? __ldg(s2 + s2w0 + k) : (uint8_t)0;
-                        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    };
+                    __syncwarp();
+                    const bool hit = (np == tp) && (ns == ts) && (tr >= nr0) && (tr <= nr1);
+                    if (hit) {
+                        cb ^= 1u;               // the prefetched window becomes the current one
+                        wp = np;
+                        ws = ns;
+                        wr0 = nr0;
+                        wr1 = nr1;
+                    } else {
+                        // drain whatever is still landing in the other buffer, then load the window that ends at this row:
+                        // rows [r-255, r] x all 32 fill-lanes of the tile
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        wp = tp;
+                        ws = ts;
+                        wr1 = tr;
+                        wr0 = (wr1 >= WR - 1) ? wr1 - (WR - 1) : 0;
+                        issue_codes(cb, wp, ws, wr0, wr1);
                     }
+                    np = 0xffffffffu;
+                    wc0 = wr0 / SPC;
+                    uint8_t *base = walk_smem + cb * BUF_BYTES;
+                    win = reinterpret_cast<const uint4 *>(base);
+                    uint8_t *s1wm = base + NCH * 32 * 16, *s2wm = s1wm + (WR + 32);
+                    s1w = s1wm;
+                    s2w = s2wm;
+                    // label characters: rows wr0..wr1 of panel wp -> s1 indices (i-1)+1, columns of strip ws -> s2 indices (j-1)+1
+                    s1w0 = (wp << PANEL_H_LOG2) + wr0 + 1u;
+                    s2w0 = ws * G::W + 1u;
+                    // (all loads first, then the stores: one memory latency for the whole window, not one per byte)
+                    {
+                        uint8_t a1[WR / 32], a2[K];
+#pragma unroll
+                        for (int q2 = 0; q2 < WR / 32; ++q2) {
+                            const uint32_t k = (uint32_t)lane + 32u * q2;
+                            a1[q2] = (k <= wr1 - wr0 && s1w0 + k < m) ? __ldg(s1 + s1w0 + k) : (uint8_t)0;
+                        }
+#pragma unroll
+                        for (int q2 = 0; q2 < K; ++q2) {
+                            const uint32_t k = (uint32_t)lane + 32u * q2;
+                            a2[q2] = (s2w0 + k < n) ? __ldg(s2 + s2w0 + k) : (uint8_t)0;
+                        }
+#pragma unroll
+                        for (int q2 = 0; q2 < WR / 32; ++q2) s1wm[lane + 32 * q2] = a1[q2];
+#pragma unroll
+                        for (int q2 = 0; q2 < K; ++q2) s2wm[lane + 32 * q2] = a2[q2];
+                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
                     c0 = cell_code(i, j);
+                    // predict the next window and start fetching it into the other buffer: a diagonal path leaves this window
+                    // on the left after (columns to the strip's left edge) rows, at the top after (rows above the entry) rows
+                    {
+                        const uint32_t cin = jj % G::W + 1u, rows_up = tr - wr0 + 1u;
+                        const bool left_ok = ws > 0, top_ok = (wr0 > 0) || (wp > 0);
+                        const bool go_left = left_ok && (cin <= rows_up || !top_ok);
+                        if (go_left) {
+                            np = wp;
+                            ns = ws - 1u;
+                            nr0 = wr0;
+                            nr1 = wr1;
+                        } else if (top_ok) {
+                            ns = ws;
+                            if (wr0 > 0) {
+                                np = wp;
+                                nr1 = wr0 - 1u;
+                                nr0 = (nr1 >= WR - 1) ? nr1 - (WR - 1) : 0;
+                            } else {
+                                np = wp - 1u;
+                                nr1 = PANEL_H - 1;
+                                nr0 = PANEL_H - WR;
+                            }
+                        }
+                        if (np != 0xffffffffu) issue_codes(cb ^ 1u, np, ns, nr0, nr1);
+                    }
                     if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;
                 }
                 if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
@@ -210,6 +285,7 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             }
             res.end_i = end_i;
             res.end_j = end_j;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         if (P.debug) {
             res.lcs_at_first_max = dbg_iters | (dbg_reloads << 32);

@@ -28,5 +28,7 @@ for q in range(min(2, len(w["len1"]))):
         o = np.argsort(s[sel])
         dp0 = (tl[sel, 1][o] - t0) / 1e3; end = (tl[sel, 2][o] - t0) / 1e3
         print(f"  pair {q} panel {pp}: strip0 dp0 {dp0[0]:8.1f} end {end[0]:8.1f} | last strip dp0 {dp0[-1]:8.1f} end {end[-1]:8.1f} | median run {np.median(end-dp0):7.1f} us, median lag {np.median(np.diff(dp0)):5.2f} us")
+top, bnd, tile, s1w, ntl = [plan.stat(k) for k in range(10, 15)]
+print(f"  in tiles: top wait {100*top/tile:.1f}%  boundary wait {100*bnd/tile:.1f}%  compute {(tile-top-bnd-s1w)/ntl/4096:.0f} clk/step (4096-row tiles)")
 busy = ((tl[:, 2] - tl[:, 1]).sum()) / 1e3
 print(f"  sum of tile run times {busy/1e3:.2f} ms over {nt} tiles; kernel {plan.fill_ms:.2f} ms; distinct SMs used {len(set(sm.tolist()))}")
