@@ -41,6 +41,8 @@ struct Ctx {
     int *lane_scores_host[2] = {nullptr, nullptr};   // pinned
     uint4 *lane_rec_host[2] = {nullptr, nullptr};    // pinned: per-pair records of the chunk in flight
     size_t lane_scores_cap = 0;
+    uint8_t *ops_stage = nullptr;                     // pinned D2H staging of op lists (grown on demand)
+    size_t ops_stage_cap = 0;
     std::string last_error;
     size_t pool_bytes = 0;
 };
@@ -167,7 +169,6 @@ struct gx_plan {
     float fill_ms = 0, walk_ms = 0;
     int launches = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0, dev_bytes = 0;
-    std::vector<uint8_t> ops_stage;
     // band plans (gx_band_*): every "pair" is a column band of one wide table
     gx_band *band = nullptr;
 };
@@ -349,6 +350,7 @@ void gx_shutdown(void) {
         if (g_ctx->lane_scores_host[k]) cudaFreeHost(g_ctx->lane_scores_host[k]);
         if (g_ctx->lane_rec_host[k]) cudaFreeHost(g_ctx->lane_rec_host[k]);
     }
+    if (g_ctx->ops_stage) cudaFreeHost(g_ctx->ops_stage);
     cudaStreamDestroy(g_ctx->stream);
     delete g_ctx;
     g_ctx = nullptr;
@@ -765,12 +767,29 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
         int nsym = 0;
         uint8_t lut[256];
         memset(lut, 255, sizeof lut);
-        for (uint64_t q = 0; q < pl->n_pairs && nsym <= 4; ++q) {
-            const uint8_t *a = blob + off1[q], *b = blob + off2[q];
-            for (uint64_t k = 0; k < pl->len1[q]; ++k)
-                if (!seen[a[k]]) { seen[a[k]] = true; if (nsym < 4) lut[a[k]] = (uint8_t)nsym; nsym++; }
-            for (uint64_t k = 0; k < pl->len2[q]; ++k)
-                if (!seen[b[k]]) { seen[b[k]] = true; if (nsym < 4) lut[b[k]] = (uint8_t)nsym; nsym++; }
+        {
+            // every distinct (offset, length) segment once -- all-vs-all batches reuse the same few sequences many times
+            std::vector<std::pair<uint64_t, uint64_t>> segs;
+            segs.reserve(2 * pl->n_pairs);
+            for (uint64_t q = 0; q < pl->n_pairs; ++q) {
+                segs.push_back({off1[q], pl->len1[q]});
+                segs.push_back({off2[q], pl->len2[q]});
+            }
+            std::sort(segs.begin(), segs.end());
+            segs.erase(std::unique(segs.begin(), segs.end()), segs.end());
+            uint64_t done_to = 0;   // bytes below this offset have been scanned (segments sorted by offset)
+            for (size_t k = 0; k < segs.size() && nsym <= 4; ++k) {
+                uint64_t lo = std::max(segs[k].first, done_to), hi = segs[k].first + segs[k].second;
+                for (uint64_t x = lo; x < hi; ++x) {
+                    const uint8_t ch = blob[x];
+                    if (!seen[ch]) {
+                        seen[ch] = true;
+                        if (nsym < 4) lut[ch] = (uint8_t)nsym;
+                        nsym++;
+                    }
+                }
+                done_to = std::max(done_to, hi);
+            }
         }
         pl->prof = nsym <= 4 && pl->n_tiles > 0;
         if (pl->prof) {
@@ -1012,8 +1031,18 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
     CK(cudaMemcpyAsync(out, pl->d_results, pl->n_pairs * sizeof(gx_result), cudaMemcpyDeviceToHost, c->stream));
     pl->d2h_bytes = pl->n_pairs * sizeof(gx_result);
     if (pl->traceback) {
-        pl->ops_stage.resize(pl->ops_bytes);
-        CK(cudaMemcpyAsync(pl->ops_stage.data(), pl->d_ops, pl->ops_bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (c->ops_stage_cap < pl->ops_bytes) {
+            if (c->ops_stage) cudaFreeHost(c->ops_stage);
+            c->ops_stage = nullptr;
+            c->ops_stage_cap = 0;
+            const size_t want = pl->ops_bytes + pl->ops_bytes / 4 + 4096;
+            if (cudaHostAlloc((void **)&c->ops_stage, want, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return GX_ERR_NOMEM;
+            }
+            c->ops_stage_cap = want;
+        }
+        CK(cudaMemcpyAsync(c->ops_stage, pl->d_ops, pl->ops_bytes, cudaMemcpyDeviceToHost, c->stream));
         pl->d2h_bytes += pl->ops_bytes;
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1028,7 +1057,7 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
                 rc = GX_ERR_OPS_CAP;
                 continue;
             }
-            memcpy(ops_blob + ops_off[q], pl->ops_stage.data() + pl->pairs[q].ops_off, out[q].n_ops);
+            memcpy(ops_blob + ops_off[q], c->ops_stage + pl->pairs[q].ops_off, out[q].n_ops);
         }
     }
     return rc;
