@@ -212,14 +212,14 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     kern = (track_override >= 0) ? pick_fill<K>(pl->prof, pl->chain1, L, false, track_override)
                                  : pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
     // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
-    int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * WARPS_PER_SM) ? WARPS_PER_CTA : 1;
+    int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * warps_per_sm(K)) ? WARPS_PER_CTA : 1;
     if (const char *e = getenv("GX_WPC")) wpc = atoi(e) == 1 ? 1 : WARPS_PER_CTA;
     const size_t smem = (size_t)wpc * warp_smem_bytes(K);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * warp_smem_bytes(K))));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
     if (occ < 1) occ = 1;
-    occ = std::min(occ, WARPS_PER_SM / wpc);
+    occ = std::min(occ, warps_per_sm(K) / wpc);
     uint64_t want = (pl->n_tiles + wpc - 1) / wpc;
     uint64_t cap = (uint64_t)c->sm_count * occ;
     if (getenv("GX_GRID_CAP")) grid_cap = atoi(getenv("GX_GRID_CAP"));
@@ -467,7 +467,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     // ---- wavefront geometry: K columns per lane.  Larger K amortises the per-step hand-off over more cells,
     // smaller K gives more strips (warps) for batches that cannot fill the GPU otherwise.
     {
-        const uint64_t resident = (uint64_t)c->sm_count * WARPS_PER_SM;
+        const uint64_t resident = (uint64_t)c->sm_count * warps_per_sm(16);   // thresholds below were tuned against 16 warps per SM
         uint64_t strips16 = 0, strips8 = 0;
         for (uint64_t q = 0; q < n_pairs; ++q)
             if (len1[q] && len2[q]) {

@@ -17,8 +17,11 @@ constexpr int PANEL_H = 1 << PANEL_H_LOG2;
 // with every warp slot busy the 8-warp shape is a few per cent faster.  gx_api.cu picks the shape per plan.
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int CTAS_PER_SM = 2;    // at 8 warps: 128 registers per thread
-constexpr int WARPS_PER_SM = WARPS_PER_CTA * CTAS_PER_SM;
+// 8-warp CTAs per SM: 2 (16 warps, 128 registers per thread) for every K.  Tried: 3 CTAs (24 warps, 80 registers)
+// for K <= 8 to have more warps covering the ones that wait for their left neighbour -- slower everywhere
+// (corona45 K=8 18.2 -> 20.9 ms, 1 Mbp x 1 Mbp 322 -> 373 ms): the register cap costs more than the occupancy gives.
+__host__ __device__ constexpr int ctas_per_sm(int K) { return K > 0 ? 2 : 2; }
+__host__ __device__ constexpr int warps_per_sm(int K) { return WARPS_PER_CTA * ctas_per_sm(K); }
 
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
 // the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.

@@ -251,7 +251,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
 }
 
 template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
-__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) gx_fill_kernel(const FillParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(const FillParams P) {
     using G = Geo<K>;
     constexpr int W = G::W;
     constexpr int B = G::BATCH;
