@@ -147,6 +147,9 @@ struct gx_plan {
     bool prof = false;
     gx::PairDesc *d_pairs = nullptr;
     gx::TileDesc *d_tiles = nullptr;
+    gx::TileDesc *d_strips = nullptr;   // resident-strips mode (every strip has its own warp): tiles as [strip][panel]
+    bool resident = false;
+    uint32_t pmax = 0;
     uint32_t *d_ctrl = nullptr;  // [0] ticket, [16..] progress
     unsigned long long *d_colbuf = nullptr;
     int2 *d_top = nullptr;
@@ -214,19 +217,26 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
     int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * warps_per_sm(K)) ? WARPS_PER_CTA : 1;
     if (const char *e = getenv("GX_WPC")) wpc = atoi(e) == 1 ? 1 : WARPS_PER_CTA;
+    if (pl->resident) wpc = 1;   // one strip per single-warp CTA, dealt round-robin over the SMs
     const size_t smem = (size_t)wpc * warp_smem_bytes(K);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * warp_smem_bytes(K))));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem));
     if (occ < 1) occ = 1;
     occ = std::min(occ, warps_per_sm(K) / wpc);
-    uint64_t want = (pl->n_tiles + wpc - 1) / wpc;
     uint64_t cap = (uint64_t)c->sm_count * occ;
+    FillParams fq = fp;
+    if (pl->resident && pl->n_strips <= cap) {   // every strip resident: static ownership, tiles as [strip][panel]
+        fq.pmax = pl->pmax;
+        fq.tiles = pl->d_strips;
+        fq.n_tiles = (uint32_t)(pl->n_strips * pl->pmax);
+    }
+    uint64_t want = fq.pmax ? pl->n_strips : (pl->n_tiles + wpc - 1) / wpc;
     if (getenv("GX_GRID_CAP")) grid_cap = atoi(getenv("GX_GRID_CAP"));
     if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
     int grid = (int)std::min<uint64_t>(want, cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, wpc * 32, smem, c->stream>>>(fp);
+    kern<<<grid, wpc * 32, smem, c->stream>>>(fq);
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -255,7 +265,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best, pl->d_first, pl->d_masks, pl->d_carry,
+    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_strips, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best, pl->d_first, pl->d_masks, pl->d_carry,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -550,6 +560,20 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         delete pl;
         return GX_ERR_RANGE;
     }
+    // resident-strips mode: every strip of the plan fits a warp slot of its own (16 warps per SM)
+    std::vector<TileDesc> strips;
+    {
+        uint64_t ns = 0;
+        for (uint64_t q = 0; q < n_pairs; ++q) ns += pl->pairs[q].S;
+        pl->resident = ns > 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K) && !getenv("GX_TICKETS");
+        if (pl->resident) {
+            for (uint64_t q = 0; q < n_pairs; ++q) pl->pmax = std::max(pl->pmax, pl->pairs[q].P);
+            for (uint64_t q = 0; q < n_pairs; ++q)
+                for (uint32_t s2 = 0; s2 < pl->pairs[q].S; ++s2)
+                    for (uint32_t p2 = 0; p2 < pl->pmax; ++p2)
+                        strips.push_back(p2 < pl->pairs[q].P ? TileDesc{(uint32_t)q, p2, s2, 0u} : TileDesc{0xffffffffu, 0u, 0u, 0u});
+        }
+    }
     pl->code_bytes = codes;
     pl->ops_bytes = ops;
     pl->colbuf_entries = colbuf;
@@ -559,6 +583,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
 
     A(n_pairs * sizeof(PairDesc), (void **)&pl->d_pairs);
     A(tiles.size() * sizeof(TileDesc), (void **)&pl->d_tiles);
+    if (pl->resident) A(strips.size() * sizeof(TileDesc), (void **)&pl->d_strips);
     A((16 + progress) * 4, (void **)&pl->d_ctrl);
     A(colbuf * 8, (void **)&pl->d_colbuf);
     A(top * 8, (void **)&pl->d_top);
@@ -574,6 +599,8 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     if (pl->traceback) A(ops, (void **)&pl->d_ops);
     if (rc == GX_OK && !tiles.empty()) {
         cudaError_t e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && pl->resident)
+            e = cudaMemcpyAsync(pl->d_strips, strips.data(), strips.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail_cuda(e, "upload tiles");
     }
@@ -898,7 +925,7 @@ int gx_plan_execute(gx_plan *pl) {
         fp.stats = pl->d_stats;
         if (atoi(getenv("GX_FILL_STATS")) >= 2) {
             if (!pl->d_timeline) {
-                int rc = pool_alloc(c, (pl->n_tiles + 1) * 32, (void **)&pl->d_timeline);
+                int rc = pool_alloc(c, (std::max<uint64_t>(pl->n_tiles, pl->n_strips * pl->pmax) + 1) * 32, (void **)&pl->d_timeline);
                 if (rc) return rc;
             }
             fp.timeline = pl->d_timeline;
@@ -907,6 +934,7 @@ int gx_plan_execute(gx_plan *pl) {
     fp.pairs = pl->d_pairs;
     fp.tiles = pl->d_tiles;
     fp.n_tiles = (uint32_t)pl->n_tiles;
+    fp.pmax = 0;   // launch_fill switches to the [strip][panel] list when every strip gets a warp
     fp.parity = pl->parity;
     fp.epoch = bd ? bd->epoch + 1 : 0;
     fp.ticket = pl->d_ctrl;

@@ -281,16 +281,32 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
     bool dead = false;
     const uint8_t *seq = PROF ? P.blob_sym : P.blob;   // PROF: sequences re-encoded to symbols 0..3 (gx_encode_kernel)
 
+    // Two ways to hand tiles to warps:
+    //   tickets          (more strips than resident warps) every free warp draws the next tile of the dependency-ordered list;
+    //   resident strips  (P.pmax != 0: every strip of the plan has a warp of its own) warp g owns strip g for all
+    //                    of its panels.  The strips of a pair form a chain that runs at the pace of its slowest member, so
+    //                    what matters is that no scheduler holds more busy warps than the others: consecutive strips go to
+    //                    consecutive CTAs, which the block scheduler deals round-robin over the SMs -- with tickets the
+    //                    strip-to-scheduler assignment is re-drawn at every panel and some scheduler always ends up with 4.
+    // (resident mode: the tile list is laid out [strip][panel], padded to P.pmax panels per strip)
+    const uint32_t wg = blockIdx.x * (blockDim.x >> 5) + (uint32_t)wib;   // global warp index
+    uint32_t own = 0;
     for (;;) {
         uint32_t tk = 0;
-        if (lane == 0) tk = atomicAdd(P.ticket, 1u);
-        tk = __shfl_sync(FULL, tk, 0);
+        if (P.pmax != 0u) {
+            if (own >= P.pmax) break;
+            tk = wg * P.pmax + own++;
+        } else {
+            if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+            tk = __shfl_sync(FULL, tk, 0);
+        }
         if (tk >= P.n_tiles) break;
+        const TileDesc td = P.tiles[tk];
+        if (td.pair == 0xffffffffu) break;      // padding: this strip has fewer panels
         const long long st_t0 = P.stats ? clock64() : 0;
         const unsigned long long tl_take = P.stats ? globaltimer_ns() : 0ull;
         unsigned long long tl_dp0 = 0ull;
         long long st_top = 0, st_bnd = 0, st_s1 = 0;
-        const TileDesc td = P.tiles[tk];
         const PairDesc *pd = P.pairs + td.pair;
         const int m = (int)pd->m, n = (int)pd->n, S = (int)pd->S;
         const int p = (int)td.p, s = (int)td.s;

@@ -9,4 +9,4 @@ run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 run --workload nw1m --steps 3 --warmup 2 --no-k0 > gpurun_out/bench_nw1m_n$N.json 2> gpurun_out/bench_nw1m_n$N.err
 run --workload corona45 --steps 10 --warmup 3 --no-k0 > gpurun_out/bench_corona45_n$N.json 2> gpurun_out/bench_corona45_n$N.err
 run --workload reads150 --pairs 10000000 --steps 5 --warmup 3 --no-k0 > gpurun_out/bench_reads10m_n$N.json 2> gpurun_out/bench_reads10m_n$N.err
-tail -c 1500 gpurun_out/bench_*_n$N.json; tail -5 gpurun_out/bench_*_n$N.err
+tail -c 1500 gpurun_out/bench_*_n$N.json; tail -n 5 gpurun_out/bench_nw1m_n$N.err
