@@ -226,7 +226,11 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     occ = std::min(occ, warps_per_sm(K) / wpc);
     uint64_t cap = (uint64_t)c->sm_count * occ;
     FillParams fq = fp;
-    if (pl->resident && pl->n_strips <= cap) {   // every strip resident: static ownership, tiles as [strip][panel]
+    if (pl->resident && pl->n_strips > cap) {
+        g_err = "resident-strips plan does not fit the device (fewer than 16 single-warp CTAs per SM)";
+        return GX_ERR_INTERNAL;
+    }
+    if (pl->resident) {   // every strip resident: static ownership, tiles as [strip][panel]
         fq.pmax = pl->pmax;
         fq.tiles = pl->d_strips;
         fq.n_tiles = (uint32_t)(pl->n_strips * pl->pmax);
@@ -506,7 +510,8 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     const uint32_t SPC = 64u / (uint32_t)K, BATCH = SPC > 8 ? SPC : 8, CPB = BATCH / SPC;
     pl->pairs.resize(n_pairs);
     std::vector<TileDesc> tiles;
-    std::vector<uint64_t> keys;
+    std::vector<uint64_t> sbase(n_pairs, 0);
+    uint64_t n_tiles_total = 0;
     uint64_t colbuf = 0, top = 0, codes = 0, ops = 0, progress = 0, best = 0;
     uint64_t strip_base = 0;   // band plans: strips of all bands form one sequence
     for (uint64_t q = 0; q < n_pairs; ++q) {
@@ -539,33 +544,51 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
             if (pl->traceback) codes += (uint64_t)pd.S * pd.P * pd.tile_code_bytes;
         }
         if (pl->traceback) ops += ((m + n + 1) + 31) & ~uint64_t(31);
-        // ticket order: every dependency of (p,s) -- (p,s-1) and (p-1,s) -- gets a smaller key.
-        for (uint32_t p = 0; p < pd.P; ++p)
-            for (uint32_t s = 0; s < pd.S; ++s) {
-                tiles.push_back({(uint32_t)q, p, s, 0});
-                keys.push_back(((uint64_t)p * PANEL_H + (strip_base + s) * 64) << 24 | (q & 0xffffff));
-            }
+        sbase[q] = strip_base;
+        n_tiles_total += (uint64_t)pd.S * pd.P;
         if (band_col0) strip_base += pd.S;
     }
-    {
-        std::vector<uint32_t> idx(tiles.size());
-        for (size_t k = 0; k < idx.size(); ++k) idx[k] = (uint32_t)k;
-        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-        std::vector<TileDesc> sorted(tiles.size());
-        for (size_t k = 0; k < idx.size(); ++k) sorted[k] = tiles[idx[k]];
-        tiles.swap(sorted);
-    }
-    pl->n_tiles = tiles.size();
-    if (pl->n_tiles >= (1ull << 32) - 65536) {
+    if (n_tiles_total >= (1ull << 32) - 65536) {
         delete pl;
         return GX_ERR_RANGE;
     }
-    // resident-strips mode: every strip of the plan fits a warp slot of its own (16 warps per SM)
-    std::vector<TileDesc> strips;
+    // resident-strips mode: every strip of the plan fits a warp slot of its own (single-warp CTAs, 16 per SM: the
+    // launch bounds cap the registers at 128 and 16 x (per-warp shared memory + 1 KB) fits the SM for every K)
     {
         uint64_t ns = 0;
         for (uint64_t q = 0; q < n_pairs; ++q) ns += pl->pairs[q].S;
         pl->resident = ns > 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K) && !getenv("GX_TICKETS");
+    }
+    if (!pl->resident) {
+        // ticket order: key(p,s) = p*4096 + (strip_base+s)*64, ties by pair then panel -- every dependency of (p,s),
+        // (p,s-1) and (p-1,s), gets a smaller key.  Generated in order (no sort): v = key / 64 = 64 p + strip_base + s.
+        tiles.reserve(n_tiles_total);
+        uint64_t vmax = 0;
+        for (uint64_t q = 0; q < n_pairs; ++q)
+            if (pl->pairs[q].S) vmax = std::max<uint64_t>(vmax, (uint64_t)(pl->pairs[q].P - 1) * 64 + sbase[q] + pl->pairs[q].S - 1);
+        // pairs that have tiles at all, so that the sweep over v costs O(tiles + live pairs x v)
+        std::vector<uint32_t> live;
+        for (uint64_t q = 0; q < n_pairs; ++q)
+            if (pl->pairs[q].S) live.push_back((uint32_t)q);
+        for (uint64_t v = 0; v <= vmax && !live.empty(); ++v) {
+            size_t keep = 0;
+            for (size_t li = 0; li < live.size(); ++li) {
+                const uint32_t q = live[li];
+                const PairDesc &pd = pl->pairs[q];
+                const uint64_t last = (uint64_t)(pd.P - 1) * 64 + sbase[q] + pd.S - 1;
+                if (v <= last) live[keep++] = q;      // still has tiles at or after v
+                if (v < sbase[q]) continue;
+                const uint64_t sv = v - sbase[q];
+                const uint64_t p_hi = std::min<uint64_t>(pd.P - 1, sv / 64);
+                const uint64_t p_lo = (sv >= pd.S) ? (sv - pd.S + 1 + 63) / 64 : 0;
+                for (uint64_t p2 = p_lo; p2 <= p_hi; ++p2) tiles.push_back({q, (uint32_t)p2, (uint32_t)(sv - 64 * p2), 0});
+            }
+            live.resize(keep);
+        }
+    }
+    pl->n_tiles = n_tiles_total;
+    std::vector<TileDesc> strips;
+    {
         if (pl->resident) {
             for (uint64_t q = 0; q < n_pairs; ++q) pl->pmax = std::max(pl->pmax, pl->pairs[q].P);
             for (uint64_t q = 0; q < n_pairs; ++q)
@@ -597,8 +620,9 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     }
     A(n_pairs * sizeof(DevResult), (void **)&pl->d_results);
     if (pl->traceback) A(ops, (void **)&pl->d_ops);
-    if (rc == GX_OK && !tiles.empty()) {
-        cudaError_t e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
+    if (rc == GX_OK && (!tiles.empty() || !strips.empty())) {
+        cudaError_t e = cudaSuccess;
+        if (!tiles.empty()) e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess && pl->resident)
             e = cudaMemcpyAsync(pl->d_strips, strips.data(), strips.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
