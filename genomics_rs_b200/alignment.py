@@ -183,8 +183,8 @@ assert RESULT_DTYPE.itemsize == C.sizeof(_lib.GxResult)
 class DeviceTable:
     """What `alignment_table` hands to `retrace`: an executed plan for one pair (codes stay in HBM)."""
 
-    def __init__(self, plan: Plan, s1: Sequence, s2: Sequence, is_local: bool):
-        self.plan, self.s1, self.s2, self.is_local = plan, s1, s2, is_local
+    def __init__(self, plan: Plan, s1: Sequence, s2: Sequence, is_local: bool, scores=None):
+        self.plan, self.s1, self.s2, self.is_local, self.scores = plan, s1, s2, is_local, scores
 
     @property
     def shape(self) -> Tuple[int, int]:
@@ -213,11 +213,14 @@ def alignment_table(sequence_container: SequenceContainer, scores, is_local: boo
     if matches_at_max:
         res, _, _ = plan.fetch()
         second = int(res[0]["lcs_at_first_max"])
-    return DeviceTable(plan, s1, s2, is_local), second
+    return DeviceTable(plan, s1, s2, is_local, scores), second
 
 
-def retrace(sequence_container: SequenceContainer, alignment_table_: DeviceTable, is_local: bool) -> AlignedSequences:
-    """algo.rs:287-441.  The walk already ran on the device; this fetches ops, counters and score."""
+def retrace(sequence_container: SequenceContainer, alignment_table_: DeviceTable, is_local: bool,
+            print_table: bool = False) -> AlignedSequences:
+    """algo.rs:287-441.  The walk already ran on the device; this fetches ops, counters and score.
+    print_table=True reproduces the reference's side effect at algo.rs:438: for small inputs (s1 < 200, s2 < 2000
+    characters) the path grid and the three score planes go to stdout (display.rs:131-220)."""
     t = alignment_table_
     if bool(is_local) != bool(t.is_local):
         raise ValueError("retrace called with a different is_local than alignment_table")
@@ -234,6 +237,13 @@ def retrace(sequence_container: SequenceContainer, alignment_table_: DeviceTable
     log.info("Retrace complete, time taken: %dus", int(out.walk_ms * 1000))
     log.info("Retrace alignment size: %d", n)
     t.plan.close()
+    if print_table:
+        from .display import DISP_MAX_WIDTH, format_alignment_table
+        b1, b2 = _as_u8(t.s1.sequence), _as_u8(t.s2.sequence)
+        if b1.size < DISP_MAX_WIDTH and b2.size < DISP_MAX_WIDTH * 10 and t.scores is not None:
+            print(format_alignment_table(out, score_planes(b1, b2, t.scores, is_local)), end="")
+        else:
+            log.warning("Sequence table too large to visualize")
     return out
 
 
@@ -300,6 +310,17 @@ def align_all(sequence_container: SequenceContainer, scores, is_local: bool, tra
     out = align_batch([(seqs[a].sequence, seqs[b].sequence) for a, b in jobs], scores, is_local, traceback=traceback,
                       names=[(seqs[a].name, seqs[b].name) for a, b in jobs])
     return list(zip(jobs, out))
+
+
+def score_planes(s1, s2, scores, is_local: bool):
+    """(insert, delete, sub) score planes of the table, (m+1) x (n+1) int64 each, as the reference's small-table
+    visualiser prints them (display.rs:190-220).  gx_debug_planes: m < 200 and n < 2000 like the reference."""
+    lib = _lib.ensure_init()
+    a, b = _as_u8(s1), _as_u8(s2)
+    out = [np.zeros((a.size + 1, b.size + 1), np.int64) for _ in range(3)]
+    _lib.check(lib.gx_debug_planes(a.ctypes.data if a.size else None, a.size, b.ctypes.data if b.size else None, b.size,
+                                   _scores_struct(scores), int(bool(is_local)), *[o.ctypes.data for o in out]))
+    return tuple(out)
 
 
 def score_batch(blob: np.ndarray, off1, len1, off2, len2, scores, is_local: bool, out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -557,7 +557,10 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     {
         uint64_t ns = 0;
         for (uint64_t q = 0; q < n_pairs; ++q) ns += pl->pairs[q].S;
-        pl->resident = ns > 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K) && !getenv("GX_TICKETS");
+        // measured: 41 % of the warp slots (980 strips) 96 -> 76 ms, 60 % (6 corona pairs) 5.5 -> 4.6 ms, 83 % (1954 strips)
+        // 352 -> 357 ms: with most slots busy the ticket order's interleaving of panels does as well, so stop at 70 %
+        pl->resident = ns > 0 && ns * 10 <= (uint64_t)c->sm_count * warps_per_sm(K) * 7 && !getenv("GX_TICKETS");
+        if (getenv("GX_RESIDENT") && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = atoi(getenv("GX_RESIDENT")) != 0;
     }
     if (!pl->resident) {
         // ticket order: key(p,s) = p*4096 + (strip_base+s)*64, ties by pair then panel -- every dependency of (p,s),
@@ -1394,6 +1397,55 @@ int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_
     if (!rc) rc = gx_band_execute(b);
     if (!rc) rc = gx_band_score(b, score, &valid);
     gx_band_destroy(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-table visualiser support: display.rs:131-220 prints the path grid and the three score planes
+int gx_debug_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local, int64_t *ins,
+                    int64_t *del, int64_t *sub) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!ins || !del || !sub || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
+    if (!g_ctx) return GX_ERR_NOT_INIT;
+    if (!(m < 200 && n < 2000)) return GX_ERR_RANGE;     // display.rs:139: "Sequence table too large to visualize"
+    int rc = check_scores_impl(sc, m, n, is_local != 0);
+    if (rc) return rc;
+    Ctx *c = g_ctx;
+    CK(cudaSetDevice(c->device));
+    const size_t cells = (size_t)(m + 1) * (n + 1);
+    uint8_t *d_seq = nullptr;
+    long long *d_planes = nullptr;
+    rc = pool_alloc(c, m + n + 16, (void **)&d_seq);
+    if (!rc) rc = pool_alloc(c, 3 * cells * 8, (void **)&d_planes);
+    if (!rc) {
+        cudaError_t e = cudaSuccess;
+        if (m) e = cudaMemcpyAsync(d_seq, s1, m, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_seq + m, s2, n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            PlanesParams pp;
+            pp.s1 = d_seq;
+            pp.s2 = d_seq + m;
+            pp.m = (uint32_t)m;
+            pp.n = (uint32_t)n;
+            pp.a = sc.s_match;
+            pp.b = sc.s_mismatch;
+            pp.g = sc.g;
+            pp.h = sc.h;
+            pp.is_local = is_local ? 1 : 0;
+            pp.pi = d_planes;
+            pp.pd = d_planes + cells;
+            pp.ps = d_planes + 2 * cells;
+            gx_planes_kernel<<<1, 256, 0, c->stream>>>(pp);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ins, d_planes, cells * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(del, d_planes + cells, cells * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sub, d_planes + 2 * cells, cells * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "gx_debug_planes");
+    }
+    pool_free(c, d_seq);
+    pool_free(c, d_planes);
     return rc;
 }
 

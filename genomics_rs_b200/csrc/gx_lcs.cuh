@@ -161,4 +161,60 @@ __global__ void __launch_bounds__(32) gx_lcs_kernel(const LcsParams P) {
     if (lane == 0) P.results[q].lcs_at_first_max = zeros;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small-table visualiser support: the three score planes print_scores_table prints
+// (/root/reference/src/alignment/display.rs:190-220), i.e. insert_score / delete_score / sub_score of every cell exactly
+// as alignment_table stores them (algo.rs:195-248), int64, boundary "minus infinity" = i64::MIN + |g+h| (algo.rs:166).
+// The reference only prints tables with m < 200 and n < 2000, so one CTA sweeping the anti-diagonals is plenty.
+struct PlanesParams {
+    const uint8_t *s1, *s2;
+    uint32_t m, n;
+    long long a, b, g, h;
+    int is_local;
+    long long *pi, *pd, *ps;     // row-major (m+1) x (n+1)
+};
+
+__device__ __forceinline__ long long planes_mx(long long I, long long S, long long D, long long x, long long y, long long z, bool local) {
+    // ComputeScore::score_max (algo.rs:98-107): max(I+x, S+y, D+z, local ? 0 : i64::MIN), wrapping adds
+    const long long vi = (long long)((unsigned long long)I + (unsigned long long)x);
+    const long long vs = (long long)((unsigned long long)S + (unsigned long long)y);
+    const long long vd = (long long)((unsigned long long)D + (unsigned long long)z);
+    long long v = vi > vs ? vi : vs;
+    v = v > vd ? v : vd;
+    const long long f = local ? 0ll : (long long)0x8000000000000000ull;
+    return v > f ? v : f;
+}
+
+__global__ void __launch_bounds__(256) gx_planes_kernel(const PlanesParams P) {
+    const uint32_t C = P.n + 1;
+    const long long gh = P.g + P.h;
+    const long long neg_inf = (long long)(0x8000000000000000ull + (unsigned long long)(gh < 0 ? -gh : gh));
+    const bool local = P.is_local != 0;
+    for (uint32_t d = 0; d <= P.m + P.n; ++d) {
+        for (uint32_t i = threadIdx.x; i <= P.m && i <= d; i += blockDim.x) {
+            const uint32_t j = d - i;
+            if (j > P.n) continue;
+            long long ci, cd, cs;
+            if (i == 0 && j == 0) {
+                ci = cd = cs = 0;                                   // algo.rs:195-202
+            } else if (j == 0) {
+                ci = neg_inf; cd = P.h + (long long)i * P.g; cs = neg_inf;   // algo.rs:204-211
+            } else if (i == 0) {
+                ci = P.h + (long long)j * P.g; cd = neg_inf; cs = neg_inf;   // algo.rs:213-220
+            } else {
+                const size_t top = (size_t)i * C + (j - 1), left = (size_t)(i - 1) * C + j, tl = (size_t)(i - 1) * C + (j - 1);
+                const bool eq = P.s1[i - 1] == P.s2[j - 1];         // is_match(i-1, j-1), algo.rs:227
+                ci = planes_mx(P.pi[top], P.ps[top], P.pd[top], P.g, gh, gh, local);        // algo.rs:229-235
+                cd = planes_mx(P.pi[left], P.ps[left], P.pd[left], gh, gh, P.g, local);     // algo.rs:236-242
+                cs = (eq ? P.a : P.b) + planes_mx(P.pi[tl], P.ps[tl], P.pd[tl], 0, 0, 0, local);   // algo.rs:244-248
+            }
+            const size_t at = (size_t)i * C + j;
+            P.pi[at] = ci;
+            P.pd[at] = cd;
+            P.ps[at] = cs;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace gx

@@ -78,3 +78,53 @@ def format_alignment(a) -> str:
     ident = (a.matches / align_idx) * 100.0 if align_idx else float("nan")
     out.append(f"Percent Identity {_rust_f64(ident)}%\n")            # display.rs:120-125
     return "".join(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# print_alignment_table / print_scores_table -- display.rs:131-220 (called by retrace, algo.rs:438)
+_NEG_INF_PRINT = -9223372036854775700     # display.rs:213
+
+
+def _ansi(txt: str, code: str, bold: bool, color: bool) -> str:
+    if not color:
+        return txt
+    return f"\x1b[{'1;' if bold else ''}{code}m{txt}\x1b[0m"
+
+
+def format_scores_table(plane) -> str:
+    """display.rs:190-220 for one plane ((m+1) x (n+1) int64)"""
+    rows, cols = plane.shape
+    out = [". \t" + "".join(f"{j}\t" for j in range(cols)) + "\n"]
+    for i in range(rows):
+        vals = "".join(("-inf" if int(v) <= _NEG_INF_PRINT else str(int(v))) + "\t" for v in plane[i])
+        out.append(f"{i}\t{vals}\n")
+    return "".join(out)
+
+
+def format_alignment_table(a, planes, color: bool = False):
+    """The text print_alignment_table writes to stdout (display.rs:131-188), or None when the reference skips it
+    (s1 >= 200 or s2 >= 2000 characters: "Sequence table too large to visualize").  `planes` = (insert, delete, sub)
+    from genomics_rs_b200.score_planes().  `color` adds the ANSI colours the reference's `colored` crate emits on a
+    terminal."""
+    s1, s2 = a.s1.sequence, a.s2.sequence
+    if not (len(s1.encode("utf-8")) < DISP_MAX_WIDTH and len(s2.encode("utf-8")) < DISP_MAX_WIDTH * 10):   # display.rs:139
+        log.warning("Sequence table too large to visualize")
+        return None
+    log.info("Computing sequence table visualization...")
+    path = {}
+    for c, i, j in a.alignment:                  # .find(): the FIRST entry of the walk at (i+1, j+1) wins
+        path.setdefault((i, j), int(c))
+    glyph = {0: ("M", "32", False), 1: ("X", "31", False), 2: ("I", "34", False), 3: ("D", "36", False),
+             4: ("I", "34", True), 5: ("D", "36", True)}
+    out = ["\nSequence Table (S1 columns, S2 rows):\n\n", " " + s2 + "\n"]
+    for i, ch in enumerate(s1):
+        row = [ch]
+        for j in range(len(s2)):
+            c = path.get((i + 1, j + 1))
+            row.append("." if c is None else _ansi(*glyph[c][:2], glyph[c][2], color))
+        out.append("".join(row) + "\n")
+    ins, dele, sub = planes
+    out.append("Delete Scores\n" + format_scores_table(dele))
+    out.append("Insert Scores\n" + format_scores_table(ins))
+    out.append("Sub Scores\n" + format_scores_table(sub))
+    return "".join(out)

@@ -66,6 +66,8 @@ extern "C" {
     pub fn gx_band_destroy(band: *mut gx_band);
     pub fn gx_nw_score_banded(s1: *const u8, m: u64, s2: *const u8, n: u64, sc: gx_scores, n_bands: c_int,
                               score: *mut i64) -> c_int;
+    pub fn gx_debug_planes(s1: *const u8, m: u64, s2: *const u8, n: u64, sc: gx_scores, is_local: c_int,
+                           insert_scores: *mut i64, delete_scores: *mut i64, sub_scores: *mut i64) -> c_int;
     pub fn gx_score_batch(
         seq_blob: *const u8, blob_len: u64, off1: *const u64, len1: *const u64, off2: *const u64, len2: *const u64,
         n_pairs: u64, sc: gx_scores, is_local: c_int, scores: *mut i64,

@@ -158,6 +158,12 @@ void gx_band_destroy(gx_band *band);
 /* all bands on this process's GPU: create + upload + execute + score + destroy */
 int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score);
 
+/* ---- small-table visualiser support (display.rs:131-220, called at algo.rs:438): the insert / delete / sub score planes
+ * of the table exactly as alignment_table stores them (algo.rs:195-248), row-major (m+1) x (n+1) int64 each, boundary
+ * "minus infinity" = INT64_MIN + |g+h| (algo.rs:166).  Like the reference, only for m < 200 and n < 2000 (GX_ERR_RANGE). */
+int gx_debug_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local,
+                    int64_t *insert_scores, int64_t *delete_scores, int64_t *sub_scores);
+
 /* ---- replay helper: expands ops into (i,j) per entry exactly as algo.rs:412-417 would have pushed them. */
 int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t start_j,
                   uint32_t *ops_i, uint32_t *ops_j);

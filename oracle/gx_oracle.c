@@ -535,4 +535,33 @@ int gxo_nw_band(const uint8_t *s1, uint64_t m, const uint8_t *s2band, uint64_t n
     return 0;
 }
 
+/* The three score planes of the reference's table (what print_scores_table prints, display.rs:190-220), row-major
+ * (m+1) x (n+1) int64 each: insert_score, delete_score, sub_score exactly as alignment_table stores them
+ * (algo.rs:195-248), boundary "minus infinity" = i64::MIN + |g+h| (algo.rs:166). */
+int gxo_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n,
+               int64_t a, int64_t b, int64_t g, int64_t h, int is_local, int64_t *pi, int64_t *pd, int64_t *ps) {
+    const uint64_t C = n + 1;
+    const int64_t gh = wadd(g, h);
+    const int64_t neg_inf = wadd(INT64_MIN, gh < 0 ? -gh : gh);
+    for (uint64_t i = 0; i <= m; i++)
+        for (uint64_t j = 0; j <= n; j++) {
+            cell_t c;
+            memset(&c, 0, sizeof c);
+            if (i == 0 && j == 0) {
+            } else if (j == 0) { c.ins = neg_inf; c.del = wadd(h, (int64_t)i * g); c.sub = neg_inf; }
+            else if (i == 0) { c.ins = wadd(h, (int64_t)j * g); c.del = neg_inf; c.sub = neg_inf; }
+            else {
+                cell_t tl = { pi[(i - 1) * C + j - 1], pd[(i - 1) * C + j - 1], ps[(i - 1) * C + j - 1], 0, 0, 0 };
+                cell_t left = { pi[(i - 1) * C + j], pd[(i - 1) * C + j], ps[(i - 1) * C + j], 0, 0, 0 };
+                cell_t top = { pi[i * C + j - 1], pd[i * C + j - 1], ps[i * C + j - 1], 0, 0, 0 };
+                int eq = is_match(s1, m, s2, n, i - 1, j - 1);
+                c.ins = score_max(&top, g, gh, gh, is_local);
+                c.del = score_max(&left, gh, gh, g, is_local);
+                c.sub = wadd(eq ? a : b, score_max(&tl, 0, 0, 0, is_local));
+            }
+            pi[i * C + j] = c.ins; pd[i * C + j] = c.del; ps[i * C + j] = c.sub;
+        }
+    return 0;
+}
+
 uint64_t gxo_sizeof_result(void) { return sizeof(gxo_result); }

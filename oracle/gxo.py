@@ -92,6 +92,9 @@ def _bind(lib):
     lib.gxo_nw_band.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64p]
     lib.gxo_nw_band.restype = C.c_int
+    lib.gxo_planes.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gxo_planes.restype = C.c_int
     lib.gxo_hash_ops.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.gxo_hash_ops.restype = C.c_uint64
     lib.gxo_sizeof_result.restype = C.c_uint64
@@ -209,6 +212,16 @@ def nw_band(s1, s2_band, col0: int, scores, left=None):
     if rc:
         raise RuntimeError(f"oracle band status {rc}")
     return int(sc.value), (out_v, out_i)
+
+
+def planes(s1, s2, scores, is_local: bool):
+    """(insert, delete, sub) score planes of the reference's table, (m+1) x (n+1) int64 each"""
+    a1, a2 = _bytes(s1), _bytes(s2)
+    out = [np.zeros((a1.size + 1, a2.size + 1), np.int64) for _ in range(3)]
+    rc = lib().gxo_planes(_ptr(a1), a1.size, _ptr(a2), a2.size, *[int(x) for x in scores], int(is_local), *[_ptr(o) for o in out])
+    if rc:
+        raise RuntimeError(f"oracle planes status {rc}")
+    return tuple(out)
 
 
 def hash_ops(ops: np.ndarray, start: Tuple[int, int]) -> int:

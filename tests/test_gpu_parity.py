@@ -254,6 +254,28 @@ def test_align_all_directory(gx, goldens, tmp_path):
         assert [int(r[2]) for r in rows] == [gold[p]["score"] for p in ((0, 1), (0, 2), (1, 2))]
 
 
+def test_score_planes_visualiser(gx, oracle, capsys):
+    """the insert/delete/sub planes the reference's small-table visualiser prints (display.rs:131-220)"""
+    rng = np.random.default_rng(12)
+    cases = [(b"ACGT", b"AGCGT"), (b"", b"ACG"), (b"A", b""), (b"", b"")]
+    cases += [random_pair(rng, int(rng.integers(1, 199)), int(rng.integers(1, 400))) for _ in range(12)]
+    for scores in (CONFIG_TOML, TEST_CONFIG):
+        for is_local in (False, True):
+            for a, b in cases:
+                got = gx.score_planes(a, b, scores, is_local)
+                exp = oracle.planes(a, b, scores, is_local)
+                for g_, e_ in zip(got, exp):
+                    assert np.array_equal(g_, e_), (len(a), len(b), scores, is_local)
+    from genomics_rs_b200 import _lib
+    with pytest.raises(_lib.GxError):
+        gx.score_planes(b"A" * 200, b"A", CONFIG_TOML, False)          # the reference refuses these sizes too
+    sc = _container(gx, "ACGT", "AGCGT")
+    table, _ = gx.alignment_table(sc, gx.Scores(1, -2, -2, -5), False, False)
+    gx.retrace(sc, table, False, print_table=True)
+    out = capsys.readouterr().out
+    assert "Sequence Table (S1 columns, S2 rows):" in out and "AXI..." in out and "Sub Scores" in out
+
+
 def test_read_batch_scores(gx, oracle):
     """BASELINE config 4 shape: many 150 bp pairs, local score only (inter-task kernel), plus ragged lengths."""
     rng = np.random.default_rng(150)

@@ -128,3 +128,27 @@ def test_fasta_dir_ingestion(tmp_path):
     sc = gx.SequenceContainer()
     sc.from_fasta_dir(str(tmp_path))
     assert [(s.name, s.sequence) for s in sc.sequences] == [("a", "GGTT"), ("b1", "ACGT"), ("b2", "AC")]
+
+
+def test_alignment_table_visualiser_text(oracle):
+    """display.rs:131-220 with planes from the oracle (host formatting only): the reference's second test pair"""
+    import numpy as np
+    from genomics_rs_b200.display import format_alignment_table, format_scores_table
+    s1, s2, scores = "ACGT", "AGCGT", (1, -2, -2, -5)
+    o = oracle.align_faithful(s1, s2, scores, False)
+    a = gx.AlignedSequences(s1=gx.Sequence("s1", s1), s2=gx.Sequence("s2", s2), score=o.score, matches=o.matches,
+                            mismatches=o.mismatches, gap_extensions=o.gap_extensions, opening_gaps=o.opening_gaps,
+                            ops=o.ops, start=o.start, end=o.end)
+    planes = oracle.planes(s1, s2, scores, False)
+    txt = format_alignment_table(a, planes)
+    lines = txt.split("\n")
+    assert lines[1] == "Sequence Table (S1 columns, S2 rows):" and lines[3] == " AGCGT"
+    # alignment (walk order): Match(4,5) Match(3,4) Match(2,3) OpenInsert(1,2) Mismatch(1,1)  (tests/test_alignment.rs:76-89)
+    assert lines[4:8] == ["AXI...", "C..M..", "G...M.", "T....M"]
+    assert lines[8] == "Delete Scores" and lines[9] == ". \t0\t1\t2\t3\t4\t5\t"
+    assert lines[10].startswith("0\t0\t-inf\t-inf") and lines[11].startswith("1\t-7\t")
+    assert "Insert Scores" in lines and "Sub Scores" in lines
+    assert format_scores_table(np.array([[0, -9223372036854775801], [5, -3]], np.int64)) == ". \t0\t1\t\n0\t0\t-inf\t\n1\t5\t-3\t\n"
+    big = gx.AlignedSequences(s1=gx.Sequence("a", "A" * 200), s2=gx.Sequence("b", "A"), score=0, matches=0, mismatches=0,
+                              gap_extensions=0, opening_gaps=0, ops=np.zeros(0, np.uint8))
+    assert format_alignment_table(big, planes) is None      # display.rs:139-143: too large, skipped
