@@ -22,7 +22,7 @@ EXPORTS = [
     "gx_align_pair", "gx_align_batch", "gx_score_batch", "gx_plan_create", "gx_plan_upload", "gx_plan_execute",
     "gx_plan_fetch", "gx_plan_fetch_scores", "gx_plan_destroy", "gx_plan_stat", "gx_plan_debug_timeline", "gx_replay_ops", "gx_k0_measure",
     "gx_band_range", "gx_band_create", "gx_band_export", "gx_band_connect", "gx_band_upload", "gx_band_execute",
-    "gx_band_score", "gx_band_stat", "gx_band_destroy", "gx_nw_score_banded", "gx_debug_planes",
+    "gx_band_score", "gx_band_stat", "gx_band_destroy", "gx_nw_score_banded", "gx_debug_planes", "gx_debug_tile_order",
 ]
 
 
@@ -99,6 +99,7 @@ def load() -> C.CDLL:
         lib.gx_band_destroy.argtypes = [vp]; lib.gx_band_destroy.restype = None
         lib.gx_nw_score_banded.argtypes = [vp, u64, vp, u64, GxScores, i32, C.POINTER(C.c_int64)]
         lib.gx_nw_score_banded.restype = i32
+        lib.gx_debug_tile_order.argtypes = [vp, vp, u64, i32, i32, vp, u64, C.POINTER(u64)]; lib.gx_debug_tile_order.restype = i32
         lib.gx_debug_planes.argtypes = [vp, u64, vp, u64, GxScores, i32, vp, vp, vp]; lib.gx_debug_planes.restype = i32
         _lib = lib
     return _lib

@@ -397,6 +397,37 @@ int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t
 // ------------------------------------------------------------------------------------------------
 }  // extern "C"
 
+
+// Ticket order of the fill kernel's tiles: key(p,s) = p*4096 + (strip_base+s)*64, ties by pair, then panel -- every
+// dependency of (p,s), i.e. (p,s-1) and (p-1,s) (and, for column bands, the last strip of the band to the left), gets a
+// smaller ticket, so a waiting warp only ever waits for tiles that were handed out before its own.  Generated in order
+// without a sort: v = key / 64 = 64 p + strip_base + s.   S, P: strips / panels per pair; sbase: first global strip.
+static void build_ticket_order(const std::vector<uint32_t> &S, const std::vector<uint32_t> &P, const std::vector<uint64_t> &sbase,
+                               std::vector<TileDesc> &tiles) {
+    const size_t n_pairs = S.size();
+    uint64_t vmax = 0;
+    std::vector<uint32_t> live;   // pairs that still have tiles at or after v: the sweep costs O(tiles + live pairs x v)
+    for (size_t q = 0; q < n_pairs; ++q)
+        if (S[q] && P[q]) {
+            vmax = std::max<uint64_t>(vmax, (uint64_t)(P[q] - 1) * 64 + sbase[q] + S[q] - 1);
+            live.push_back((uint32_t)q);
+        }
+    for (uint64_t v = 0; v <= vmax && !live.empty(); ++v) {
+        size_t keep = 0;
+        for (size_t li = 0; li < live.size(); ++li) {
+            const uint32_t q = live[li];
+            const uint64_t last = (uint64_t)(P[q] - 1) * 64 + sbase[q] + S[q] - 1;
+            if (v <= last) live[keep++] = q;
+            if (v < sbase[q]) continue;
+            const uint64_t sv = v - sbase[q];
+            const uint64_t p_hi = std::min<uint64_t>(P[q] - 1, sv / 64);
+            const uint64_t p_lo = (sv >= S[q]) ? (sv - S[q] + 1 + 63) / 64 : 0;
+            for (uint64_t p2 = p_lo; p2 <= p_hi; ++p2) tiles.push_back({q, (uint32_t)p2, (uint32_t)(sv - 64 * p2), 0});
+        }
+        live.resize(keep);
+    }
+}
+
 // band_col0 != null: the "pairs" are consecutive column bands of one table (band q starts at column band_col0[q]);
 // their strips are ticketed as one left-to-right sequence and the short-read kernel is never chosen.
 static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
@@ -563,31 +594,13 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         if (getenv("GX_RESIDENT") && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = atoi(getenv("GX_RESIDENT")) != 0;
     }
     if (!pl->resident) {
-        // ticket order: key(p,s) = p*4096 + (strip_base+s)*64, ties by pair then panel -- every dependency of (p,s),
-        // (p,s-1) and (p-1,s), gets a smaller key.  Generated in order (no sort): v = key / 64 = 64 p + strip_base + s.
-        tiles.reserve(n_tiles_total);
-        uint64_t vmax = 0;
-        for (uint64_t q = 0; q < n_pairs; ++q)
-            if (pl->pairs[q].S) vmax = std::max<uint64_t>(vmax, (uint64_t)(pl->pairs[q].P - 1) * 64 + sbase[q] + pl->pairs[q].S - 1);
-        // pairs that have tiles at all, so that the sweep over v costs O(tiles + live pairs x v)
-        std::vector<uint32_t> live;
-        for (uint64_t q = 0; q < n_pairs; ++q)
-            if (pl->pairs[q].S) live.push_back((uint32_t)q);
-        for (uint64_t v = 0; v <= vmax && !live.empty(); ++v) {
-            size_t keep = 0;
-            for (size_t li = 0; li < live.size(); ++li) {
-                const uint32_t q = live[li];
-                const PairDesc &pd = pl->pairs[q];
-                const uint64_t last = (uint64_t)(pd.P - 1) * 64 + sbase[q] + pd.S - 1;
-                if (v <= last) live[keep++] = q;      // still has tiles at or after v
-                if (v < sbase[q]) continue;
-                const uint64_t sv = v - sbase[q];
-                const uint64_t p_hi = std::min<uint64_t>(pd.P - 1, sv / 64);
-                const uint64_t p_lo = (sv >= pd.S) ? (sv - pd.S + 1 + 63) / 64 : 0;
-                for (uint64_t p2 = p_lo; p2 <= p_hi; ++p2) tiles.push_back({q, (uint32_t)p2, (uint32_t)(sv - 64 * p2), 0});
-            }
-            live.resize(keep);
+        std::vector<uint32_t> Sv(n_pairs), Pv(n_pairs);
+        for (uint64_t q = 0; q < n_pairs; ++q) {
+            Sv[q] = pl->pairs[q].S;
+            Pv[q] = pl->pairs[q].P;
         }
+        tiles.reserve(n_tiles_total);
+        build_ticket_order(Sv, Pv, sbase, tiles);
     }
     pl->n_tiles = n_tiles_total;
     std::vector<TileDesc> strips;
@@ -1147,6 +1160,38 @@ int gx_plan_debug_timeline(gx_plan *pl, uint64_t *out, uint64_t cap_words) {
     if (!pl || !out || !pl->d_timeline || cap_words < pl->n_tiles * 4) return GX_ERR_ARG;
     CK(cudaSetDevice(pl->ctx->device));
     CK(cudaMemcpy(out, pl->d_timeline, pl->n_tiles * 32, cudaMemcpyDeviceToHost));
+    return GX_OK;
+}
+
+// Pure host arithmetic (no device): the ticket order plan_create would use for these pairs at register blocking K
+// (bands != 0: the pairs are consecutive column bands of one table).  out = {pair, panel, strip} triples.
+int gx_debug_tile_order(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, int K, int bands, uint32_t *out,
+                        uint64_t cap_tiles, uint64_t *n_tiles) {
+    if ((!len1 || !len2) && n_pairs) return GX_ERR_ARG;
+    if (!n_tiles || (K != 4 && K != 8 && K != 16)) return GX_ERR_ARG;
+    std::vector<uint32_t> S(n_pairs), P(n_pairs);
+    std::vector<uint64_t> sbase(n_pairs, 0);
+    uint64_t base = 0, total = 0;
+    for (uint64_t q = 0; q < n_pairs; ++q) {
+        const bool interior = len1[q] > 0 && len2[q] > 0;
+        S[q] = interior ? (uint32_t)((len2[q] + 32 * K - 1) / (32 * K)) : 0;
+        P[q] = interior ? (uint32_t)((len1[q] + PANEL_H - 1) / PANEL_H) : 0;
+        sbase[q] = base;
+        if (bands) base += S[q];
+        total += (uint64_t)S[q] * P[q];
+    }
+    *n_tiles = total;
+    if (!out) return GX_OK;
+    if (cap_tiles < total) return GX_ERR_ARG;
+    std::vector<TileDesc> tiles;
+    tiles.reserve(total);
+    build_ticket_order(S, P, sbase, tiles);
+    if (tiles.size() != total) return GX_ERR_INTERNAL;
+    for (size_t k = 0; k < tiles.size(); ++k) {
+        out[3 * k + 0] = tiles[k].pair;
+        out[3 * k + 1] = tiles[k].p;
+        out[3 * k + 2] = tiles[k].s;
+    }
     return GX_OK;
 }
 

@@ -164,6 +164,14 @@ int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_
 int gx_debug_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local,
                     int64_t *insert_scores, int64_t *delete_scores, int64_t *sub_scores);
 
+/* debug, pure host arithmetic (works without a GPU): the order in which the fill kernel hands out the tiles of these pairs
+ * at register blocking K in {4,8,16} (bands != 0: the pairs are consecutive column bands of one table).  out receives
+ * {pair, panel, strip} per tile (cap_tiles >= *n_tiles; out may be NULL to query the count).  Invariant (tested): the
+ * tiles a tile depends on -- (panel, strip-1), (panel-1, strip), and for bands the last strip of the band to the left
+ * -- always come earlier, which is what makes the persistent kernel deadlock-free. */
+int gx_debug_tile_order(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, int K, int bands, uint32_t *out,
+                        uint64_t cap_tiles, uint64_t *n_tiles);
+
 /* ---- replay helper: expands ops into (i,j) per entry exactly as algo.rs:412-417 would have pushed them. */
 int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t start_j,
                   uint32_t *ops_i, uint32_t *ops_j);

@@ -152,3 +152,38 @@ def test_alignment_table_visualiser_text(oracle):
     big = gx.AlignedSequences(s1=gx.Sequence("a", "A" * 200), s2=gx.Sequence("b", "A"), score=0, matches=0, mismatches=0,
                               gap_extensions=0, opening_gaps=0, ops=np.zeros(0, np.uint8))
     assert format_alignment_table(big, planes) is None      # display.rs:139-143: too large, skipped
+
+
+def test_ticket_order_respects_dependencies():
+    """the persistent fill kernel is deadlock-free because every tile's dependencies -- (panel, strip-1), (panel-1, strip)
+    and, for column bands, the last strip of the band to the left -- are handed out before it (gx_debug_tile_order
+    is the host arithmetic plan_create uses; no GPU needed)"""
+    import ctypes as C
+    import numpy as np
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    for trial in range(30):
+        bands = trial % 3 == 0
+        n_pairs = int(rng.integers(1, 9))
+        K = int(rng.choice([4, 8, 16]))
+        len2 = rng.integers(0, 6000, size=n_pairs).astype(np.uint64)
+        len1 = (np.full(n_pairs, rng.integers(1, 30000), np.uint64) if bands else rng.integers(0, 30000, size=n_pairs).astype(np.uint64))
+        if bands:
+            len2 = np.maximum(len2, 1)
+        nt = C.c_uint64()
+        assert lib.gx_debug_tile_order(len1.ctypes.data, len2.ctypes.data, n_pairs, K, int(bands), None, 0, C.byref(nt)) == 0
+        out = np.zeros(3 * max(nt.value, 1), np.uint32)
+        assert lib.gx_debug_tile_order(len1.ctypes.data, len2.ctypes.data, n_pairs, K, int(bands), out.ctypes.data, nt.value, C.byref(nt)) == 0
+        t = out[:3 * nt.value].reshape(-1, 3)
+        pos = {(int(q), int(p), int(s)): k for k, (q, p, s) in enumerate(t)}
+        assert len(pos) == nt.value                                     # every tile exactly once
+        S = [int(-(-int(len2[q]) // (32 * K))) if len1[q] and len2[q] else 0 for q in range(n_pairs)]
+        Pn = [int(-(-int(len1[q]) // 4096)) if len1[q] and len2[q] else 0 for q in range(n_pairs)]
+        assert nt.value == sum(a * b for a, b in zip(S, Pn))
+        for (q, p, s), k in pos.items():
+            if s > 0:
+                assert pos[(q, p, s - 1)] < k
+            if p > 0:
+                assert pos[(q, p - 1, s)] < k
+            if bands and s == 0 and q > 0:
+                assert pos[(q - 1, p, S[q - 1] - 1)] < k
