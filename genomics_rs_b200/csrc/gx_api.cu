@@ -954,6 +954,7 @@ int gx_plan_execute(gx_plan *pl) {
     fp.one = 1u;
     fp.stats = nullptr;
     fp.timeline = nullptr;
+    fp.pad_keys = (sc.s_mismatch >= 0 || getenv("GX_PAD_KEYS")) ? 1u : 0u;
     fp.poll_nap = getenv("GX_POLL_NAP") ? (uint32_t)atoi(getenv("GX_POLL_NAP")) : 0u;
     fp.start_lead = getenv("GX_START_LEAD") ? (uint32_t)atoi(getenv("GX_START_LEAD")) : 0u;
     if (getenv("GX_FILL_STATS")) {

@@ -78,6 +78,7 @@ struct FillParams {
     int2 *top;
     uint8_t *codes;
     int4 *tile_best;
+    uint32_t pad_keys;               // 1: padded columns of a pair's last strip could reach the maximum (s_mismatch >= 0): mask their keys
     uint32_t poll_nap;               // ns a strip sleeps between two polls of its left boundary (0: poll back to back)
     uint32_t start_lead;             // rows of extra lead a strip waits for before its first batch (slack against convoys)
     unsigned long long *timeline;    // optional with stats: 4 words per tile (debug)

@@ -593,7 +593,10 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
-            if ((TRACK != 0) && has_pad) {
+            // Columns right of the table (last strip of a pair) need their keys masked only when a padded cell could
+            // reach the maximum; with s_mismatch < 0 (and g, h+g < 0) every padded cell is strictly smaller than the real
+            // cell it derives from, so the plain body is exact -- the tile reductions ignore winners with j > n.
+            if ((TRACK != 0) && has_pad && P.pad_keys != 0u) {
                 for (; bt < nb_body && !dead; ++bt) {
                     uint2 *outr = outring + (bt & 1u) * B;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(32) gx_lcs_kernel(const LcsParams P) {
     const uint32_t ntile = pd->S * pd->P;
     for (uint32_t x = lane; x < ntile; x += 32) {
         const int4 tb = P.tile_first[pd->tile_base + x];
-        const bool take = (tb.x > bv) || (tb.x == bv && tb.x != INT32_MIN && (tb.y < bi || (tb.y == bi && tb.z < bj)));
+        const bool take = (tb.z <= (int)pd->n) && ((tb.x > bv) || (tb.x == bv && tb.x != INT32_MIN && (tb.y < bi || (tb.y == bi && tb.z < bj))));
         if (take) {
             bv = tb.x;
             bi = tb.y;

@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             const uint32_t ntile = pd->S * pd->P;
             for (uint32_t x = lane; x < ntile; x += 32) {
                 const int4 tb = P.tile_best[pd->tile_base + x];
-                const bool take = (tb.x > bv) || (tb.x == bv && (tb.y > bi || (tb.y == bi && tb.z > bj)));
+                // a winner right of the table can only come from a tile whose maximum is 0 (see gx_fill.cuh): the boundary
+                // cell (m, n) this reduction starts from covers it
+                const bool take = (tb.z <= (int)n) && ((tb.x > bv) || (tb.x == bv && (tb.y > bi || (tb.y == bi && tb.z > bj))));
                 if (take) {
                     bv = tb.x;
                     bi = tb.y;

@@ -8,7 +8,7 @@ from genomics_rs_b200 import _lib, workloads as wl
 lib = _lib.ensure_init(0)
 m, n = int(sys.argv[1]), int(sys.argv[2])
 a, b = wl.long_pair(max(m, n))
-plan = gx.Plan([m], [n], wl.CONFIG_TOML, False, traceback=False)
+plan = gx.Plan([m], [n], wl.CONFIG_TOML, os.environ.get("LOCAL", "0") == "1", traceback=os.environ.get("TB", "0") == "1")
 plan.upload(np.concatenate([a[:m], b[:n]]), [0], [m])
 for _ in range(2):
     plan.execute()
