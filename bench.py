@@ -42,7 +42,7 @@ def ncu_traffic(workload: str):
     d = json.load(open(p)).get(key)
     if not d:
         return None, None
-    return d["dram_read_bytes"] + d["dram_write_bytes"], "profiles/r1d_traffic.json (ncu --set full, one launch of the fill kernel)"
+    return d["dram_read_bytes"] + d["dram_write_bytes"], d.get("source", "profiles/r1d_traffic.json") + " (ncu --set full, one launch of the fill kernel)"
 
 
 def measured_peaks():
