@@ -58,6 +58,16 @@ static int fail_cuda(cudaError_t e, const char *what) {
     if (g_ctx) g_ctx->last_error = buf;
     return GX_ERR_CUDA;
 }
+// The C ABI never throws: entry points that allocate host memory are function-try-blocks ending in GX_GUARD_END.
+#define GX_GUARD_END                                                  \
+    catch (const std::bad_alloc &) {                                  \
+        g_err = "host allocation failed";                             \
+        return GX_ERR_NOMEM;                                          \
+    }                                                                 \
+    catch (...) {                                                     \
+        g_err = "unexpected C++ exception inside libgxalign";         \
+        return GX_ERR_INTERNAL;                                       \
+    }
 #define CK(call)                                        \
     do {                                                \
         cudaError_t e__ = (call);                       \
@@ -113,6 +123,34 @@ static void pool_free(Ctx *c, void *p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Debug / experiment switches.  The environment is read ONCE per plan (gx_plan_create) or per streamed
+// batch call, never on the execute path; -1 = not set.
+struct Tunables {
+    int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
+        fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0;
+};
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static Tunables read_tunables() {
+    Tunables t;
+    t.k = env_int("GX_K", -1);
+    t.chain1 = env_int("GX_CHAIN1", -1);
+    t.tickets = getenv("GX_TICKETS") ? 1 : -1;
+    t.resident = env_int("GX_RESIDENT", -1);
+    t.wpc = env_int("GX_WPC", -1);
+    t.grid_cap = env_int("GX_GRID_CAP", -1);
+    t.pad_keys = getenv("GX_PAD_KEYS") ? 1 : 0;
+    t.poll_nap = env_int("GX_POLL_NAP", 0);
+    t.start_lead = env_int("GX_START_LEAD", 0);
+    t.fill_stats = env_int("GX_FILL_STATS", 0);
+    t.walk_stats = getenv("GX_WALK_STATS") ? 1 : 0;
+    t.no_stream = getenv("GX_NO_STREAM") ? 1 : 0;
+    t.reads32 = getenv("GX_READS32") ? 1 : 0;
+    return t;
+}
+
 enum PlanKind { KIND_WAVEFRONT = 0, KIND_READS = 1 };
 typedef void (*FillKernel)(const FillParams);
 
@@ -124,6 +162,7 @@ struct gx_plan {
     int kind = gx::KIND_WAVEFRONT;
     uint64_t n_pairs = 0;
     gx_scores sc{};
+    gx::Tunables tun;                  // debug switches as they were when the plan was created
     int is_local = 0, flags = 0;
     int K = 8;
     bool chain1 = false;               // latency-optimised recurrence (gx_fill.cuh, CHAIN1)
@@ -216,7 +255,7 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
                                  : pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
     // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
     int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * warps_per_sm(K)) ? WARPS_PER_CTA : 1;
-    if (const char *e = getenv("GX_WPC")) wpc = atoi(e) == 1 ? 1 : WARPS_PER_CTA;
+    if (pl->tun.wpc >= 0) wpc = pl->tun.wpc == 1 ? 1 : WARPS_PER_CTA;
     if (pl->resident) wpc = 1;   // one strip per single-warp CTA, dealt round-robin over the SMs
     const size_t smem = (size_t)wpc * warp_smem_bytes(K);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS_PER_CTA * warp_smem_bytes(K))));
@@ -236,7 +275,7 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
         fq.n_tiles = (uint32_t)(pl->n_strips * pl->pmax);
     }
     uint64_t want = fq.pmax ? pl->n_strips : (pl->n_tiles + wpc - 1) / wpc;
-    if (getenv("GX_GRID_CAP")) grid_cap = atoi(getenv("GX_GRID_CAP"));
+    if (pl->tun.grid_cap >= 0) grid_cap = pl->tun.grid_cap;
     if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
     int grid = (int)std::min<uint64_t>(want, cap);
     if (grid < 1) grid = 1;
@@ -316,7 +355,7 @@ int gx_device_count(void) {
     return ok;
 }
 
-int gx_init(int device) {
+int gx_init(int device) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -350,6 +389,7 @@ int gx_init(int device) {
     g_ctx = c;
     return GX_OK;
 }
+GX_GUARD_END
 
 void gx_shutdown(void) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -454,6 +494,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     pl->ctx = c;
     pl->n_pairs = n_pairs;
     pl->sc = sc;
+    pl->tun = read_tunables();
     pl->is_local = is_local ? 1 : 0;
     pl->flags = flags;
     pl->traceback = (flags & GX_FLAG_TRACEBACK) != 0;
@@ -522,10 +563,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         // measured on corona shards (tools/timeline_wl.py): 45 pairs K=16 ~ K=8; 23 pairs K=8 ~ K=4 << K=16;
         // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
         pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
-        if (const char *e = getenv("GX_K")) {
-            const int k = atoi(e);
-            if (k == 4 || k == 8 || k == 16) pl->K = k;
-        }
+        if (pl->tun.k == 4 || pl->tun.k == 8 || pl->tun.k == 16) pl->K = pl->tun.k;
         // latency-optimised recurrence (one more ALU op per cell, 1-op row chain) when warps are too few to hide the
         // classic 3-op chain: measured win below ~1/4 of the resident warps, loss at full occupancy
         {
@@ -535,7 +573,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
             pl->chain1 = strips * 4 < resident;
             pl->n_strips = strips;
         }
-        if (const char *e = getenv("GX_CHAIN1")) pl->chain1 = atoi(e) != 0;
+        if (pl->tun.chain1 >= 0) pl->chain1 = pl->tun.chain1 != 0;
     }
     const int K = pl->K, W = 32 * K;
     const uint32_t SPC = 64u / (uint32_t)K, BATCH = SPC > 8 ? SPC : 8, CPB = BATCH / SPC;
@@ -590,8 +628,8 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         for (uint64_t q = 0; q < n_pairs; ++q) ns += pl->pairs[q].S;
         // measured: 41 % of the warp slots (980 strips) 96 -> 76 ms, 60 % (6 corona pairs) 5.5 -> 4.6 ms, 83 % (1954 strips)
         // 352 -> 357 ms: with most slots busy the ticket order's interleaving of panels does as well, so stop at 70 %
-        pl->resident = ns > 0 && ns * 10 <= (uint64_t)c->sm_count * warps_per_sm(K) * 7 && !getenv("GX_TICKETS");
-        if (getenv("GX_RESIDENT") && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = atoi(getenv("GX_RESIDENT")) != 0;
+        pl->resident = ns > 0 && ns * 10 <= (uint64_t)c->sm_count * warps_per_sm(K) * 7 && pl->tun.tickets < 0;
+        if (pl->tun.resident >= 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = pl->tun.resident != 0;
     }
     if (!pl->resident) {
         std::vector<uint32_t> Sv(n_pairs), Pv(n_pairs);
@@ -661,7 +699,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
 // no host-side repack.  Returns GX_ERR_UNSUPPORTED when the batch does not qualify (the caller falls back to a plan).
 static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1,
                                 const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local,
-                                int64_t *scores) {
+                                int64_t *scores, bool force32) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!g_ctx) return GX_ERR_NOT_INIT;
     Ctx *c = g_ctx;
@@ -702,7 +740,8 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
     auto drain = [&](int k) -> int {   // scores of the chunk that ran on lane k -> caller's int64 array
         Lane &L = lane[k];
         if (!L.busy) return GX_OK;
-        CK(cudaEventSynchronize(c->lane_done[k]));
+        cudaError_t e = cudaEventSynchronize(c->lane_done[k]);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaEventSynchronize(lane_done)");
         const int *src = c->lane_scores_host[k];
         int64_t *dst = scores + L.first;
         for (uint64_t q = 0; q < L.count; ++q) dst[q] = src[q];
@@ -713,6 +752,15 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         Lane &L = lane[k];
         rc = pool_alloc(c, CH * sizeof(uint4), (void **)&L.rec);
         if (!rc) rc = pool_alloc(c, CH * 4, (void **)&L.scores);
+    }
+    // errors inside the chunk loop leave through `break`: the lanes are drained and their pool blocks released below
+#define CKB(call)                                   \
+    {                                               \
+        cudaError_t e__ = (call);                   \
+        if (e__ != cudaSuccess) {                   \
+            rc = fail_cuda(e__, #call);             \
+            break;                                  \
+        }                                           \
     }
     for (uint64_t first = 0, ci = 0; first < n_pairs && rc == GX_OK; first += CH, ++ci) {
         const int k = (int)(ci & 1);
@@ -751,7 +799,7 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
             L.blob_cap = span + span / 4 + 64;
         }
         cudaStream_t st = c->lane_stream[k];
-        if (span) CK(cudaMemcpyAsync(L.blob, blob + lo, span, cudaMemcpyHostToDevice, st));
+        if (span) CKB(cudaMemcpyAsync(L.blob, blob + lo, span, cudaMemcpyHostToDevice, st));
         // host pass 2: 16-byte records relative to the chunk's first byte, written straight into pinned memory
         // (lane k's record buffer is free: drain(k) above waited for the chunk that used it)
         {
@@ -760,7 +808,7 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
             for (uint64_t q = 0; q < count; ++q)
                 rec[q] = make_uint4((uint32_t)(o1[q] - lo), (uint32_t)(o2[q] - lo), (uint32_t)l1[q], (uint32_t)l2[q]);
         }
-        CK(cudaMemcpyAsync(L.rec, c->lane_rec_host[k], count * sizeof(uint4), cudaMemcpyHostToDevice, st));
+        CKB(cudaMemcpyAsync(L.rec, c->lane_rec_host[k], count * sizeof(uint4), cudaMemcpyHostToDevice, st));
         ReadsParams rp;
         rp.blob = L.blob;
         rp.off1 = rp.off2 = nullptr;
@@ -774,17 +822,18 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         rp.g = sc.g;
         rp.h = sc.h;
         rp.is_local = is_local ? 1 : 0;
-        if (launch_reads(rp, (int)maxlen, c->sm_count, st) != 0) {
+        if (launch_reads(rp, (int)maxlen, c->sm_count, st, force32) != 0) {
             rc = GX_ERR_UNSUPPORTED;
             break;
         }
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(c->lane_scores_host[k], L.scores, count * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(c->lane_done[k], st));
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(c->lane_scores_host[k], L.scores, count * 4, cudaMemcpyDeviceToHost, st));
+        CKB(cudaEventRecord(c->lane_done[k], st));
         L.first = first;
         L.count = count;
         L.busy = true;
     }
+#undef CKB
     if (rc == GX_OK) rc = drain(0);
     if (rc == GX_OK) rc = drain(1);
     if (rc != GX_OK) {
@@ -799,18 +848,20 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
 extern "C" {
 
 int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags,
-                   gx_plan **out) {
+                   gx_plan **out) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     return plan_create_locked(len1, len2, n_pairs, sc, is_local, flags, nullptr, out);
 }
+GX_GUARD_END
 
-int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *off2) {
+int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *off2) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!blob && blob_len) || ((!off1 || !off2) && pl->n_pairs)) return GX_ERR_ARG;
     Ctx *c = pl->ctx;
     CK(cudaSetDevice(c->device));
-    for (uint64_t q = 0; q < pl->n_pairs; ++q)
-        if (off1[q] + pl->len1[q] > blob_len || off2[q] + pl->len2[q] > blob_len) return GX_ERR_ARG;
+    for (uint64_t q = 0; q < pl->n_pairs; ++q)   // written so that a huge offset cannot wrap around
+        if (off1[q] > blob_len || pl->len1[q] > blob_len - off1[q] || off2[q] > blob_len || pl->len2[q] > blob_len - off2[q])
+            return GX_ERR_ARG;
     if (!pl->d_blob || pl->blob_cap < blob_len + 64) {
         pool_free(c, pl->d_blob);
         pl->d_blob = nullptr;
@@ -887,8 +938,9 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
     pl->uploaded = true;
     return GX_OK;
 }
+GX_GUARD_END
 
-int gx_plan_execute(gx_plan *pl) {
+int gx_plan_execute(gx_plan *pl) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl) return GX_ERR_ARG;
     if (!pl->uploaded) return GX_ERR_ARG;
@@ -918,7 +970,7 @@ int gx_plan_execute(gx_plan *pl) {
         rp.h = sc.h;
         rp.is_local = pl->is_local;
         CK(cudaEventRecord(c->ev[0], c->stream));
-        int rc = launch_reads(rp, (int)pl->max_len, c->sm_count, c->stream);
+        int rc = launch_reads(rp, (int)pl->max_len, c->sm_count, c->stream, pl->tun.reads32 != 0);
         if (rc == -1) return GX_ERR_UNSUPPORTED;
         CK(cudaGetLastError());
         CK(cudaEventRecord(c->ev[1], c->stream));
@@ -954,17 +1006,17 @@ int gx_plan_execute(gx_plan *pl) {
     fp.one = 1u;
     fp.stats = nullptr;
     fp.timeline = nullptr;
-    fp.pad_keys = (sc.s_mismatch >= 0 || getenv("GX_PAD_KEYS")) ? 1u : 0u;
-    fp.poll_nap = getenv("GX_POLL_NAP") ? (uint32_t)atoi(getenv("GX_POLL_NAP")) : 0u;
-    fp.start_lead = getenv("GX_START_LEAD") ? (uint32_t)atoi(getenv("GX_START_LEAD")) : 0u;
-    if (getenv("GX_FILL_STATS")) {
+    fp.pad_keys = (sc.s_mismatch >= 0 || pl->tun.pad_keys) ? 1u : 0u;
+    fp.poll_nap = (uint32_t)pl->tun.poll_nap;
+    fp.start_lead = (uint32_t)pl->tun.start_lead;
+    if (pl->tun.fill_stats) {
         if (!pl->d_stats) {
             int rc = pool_alloc(c, 64, (void **)&pl->d_stats);
             if (rc) return rc;
         }
         CK(cudaMemsetAsync(pl->d_stats, 0, 64, c->stream));
         fp.stats = pl->d_stats;
-        if (atoi(getenv("GX_FILL_STATS")) >= 2) {
+        if (pl->tun.fill_stats >= 2) {
             if (!pl->d_timeline) {
                 int rc = pool_alloc(c, (std::max<uint64_t>(pl->n_tiles, pl->n_strips * pl->pmax) + 1) * 32, (void **)&pl->d_timeline);
                 if (rc) return rc;
@@ -1016,7 +1068,7 @@ int gx_plan_execute(gx_plan *pl) {
     wp.is_local = pl->is_local;
     wp.traceback = pl->traceback ? 1 : 0;
     wp.have_best = pl->track == 2 ? 1 : 0;
-    wp.debug = getenv("GX_WALK_STATS") ? 1 : 0;
+    wp.debug = pl->tun.walk_stats;
     {
         int rc = pl->K == 16 ? launch_walk<16>(pl, wp) : pl->K == 4 ? launch_walk<4>(pl, wp) : launch_walk<8>(pl, wp);
         if (rc) return rc;
@@ -1072,8 +1124,9 @@ int gx_plan_execute(gx_plan *pl) {
     pl->executed = true;
     return GX_OK;
 }
+GX_GUARD_END
 
-int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off) {
+int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!out && pl->n_pairs)) return GX_ERR_ARG;
     if (!pl->executed) return GX_ERR_ARG;
@@ -1116,7 +1169,7 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
     }
     CK(cudaStreamSynchronize(c->stream));
     int rc = GX_OK;
-    const bool walk_dbg = getenv("GX_WALK_STATS") != nullptr;
+    const bool walk_dbg = pl->tun.walk_stats != 0;
     for (uint64_t q = 0; q < pl->n_pairs; ++q) {
         if (!walk_dbg) out[q].fill_ms = pl->fill_ms;
         if (!walk_dbg) out[q].walk_ms = pl->walk_ms;
@@ -1131,8 +1184,9 @@ int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t
     }
     return rc;
 }
+GX_GUARD_END
 
-int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) {
+int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl || (!scores && pl->n_pairs)) return GX_ERR_ARG;
     if (!pl->executed) return GX_ERR_ARG;
@@ -1155,6 +1209,7 @@ int gx_plan_fetch_scores(gx_plan *pl, int64_t *scores) {
     for (uint64_t q = 0; q < pl->n_pairs; ++q) scores[q] = res[q].score;
     return GX_OK;
 }
+GX_GUARD_END
 
 int gx_plan_debug_timeline(gx_plan *pl, uint64_t *out, uint64_t cap_words) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -1167,7 +1222,7 @@ int gx_plan_debug_timeline(gx_plan *pl, uint64_t *out, uint64_t cap_words) {
 // Pure host arithmetic (no device): the ticket order plan_create would use for these pairs at register blocking K
 // (bands != 0: the pairs are consecutive column bands of one table).  out = {pair, panel, strip} triples.
 int gx_debug_tile_order(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, int K, int bands, uint32_t *out,
-                        uint64_t cap_tiles, uint64_t *n_tiles) {
+                        uint64_t cap_tiles, uint64_t *n_tiles) try {
     if ((!len1 || !len2) && n_pairs) return GX_ERR_ARG;
     if (!n_tiles || (K != 4 && K != 8 && K != 16)) return GX_ERR_ARG;
     std::vector<uint32_t> S(n_pairs), P(n_pairs);
@@ -1195,6 +1250,7 @@ int gx_debug_tile_order(const uint64_t *len1, const uint64_t *len2, uint64_t n_p
     }
     return GX_OK;
 }
+GX_GUARD_END
 
 double gx_plan_stat(const gx_plan *pl, int what) {
     if (!pl) return -1.0;
@@ -1259,7 +1315,7 @@ static void band_free(gx_band *b) {
     delete b;
 }
 
-int gx_band_create(uint64_t m, uint64_t n_total, int n_bands, int first_band, int last_band, gx_scores sc, gx_band **out) {
+int gx_band_create(uint64_t m, uint64_t n_total, int n_bands, int first_band, int last_band, gx_scores sc, gx_band **out) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!out) return GX_ERR_ARG;
     *out = nullptr;
@@ -1332,6 +1388,7 @@ int gx_band_create(uint64_t m, uint64_t n_total, int n_bands, int first_band, in
     *out = b;
     return GX_OK;
 }
+GX_GUARD_END
 
 int gx_band_export(gx_band *b, void *handle, uint64_t handle_cap) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -1346,7 +1403,7 @@ int gx_band_export(gx_band *b, void *handle, uint64_t handle_cap) {
     return GX_OK;
 }
 
-int gx_band_connect(gx_band *b, const void *left_handle, const void *right_handle) {
+int gx_band_connect(gx_band *b, const void *left_handle, const void *right_handle) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!b) return GX_ERR_ARG;
     if (b->trivial) return GX_OK;
@@ -1375,8 +1432,9 @@ int gx_band_connect(gx_band *b, const void *left_handle, const void *right_handl
     }
     return GX_OK;
 }
+GX_GUARD_END
 
-int gx_band_upload(gx_band *b, const uint8_t *s1, const uint8_t *s2) {
+int gx_band_upload(gx_band *b, const uint8_t *s1, const uint8_t *s2) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!b) return GX_ERR_ARG;
     if (b->trivial) return GX_OK;
@@ -1390,8 +1448,9 @@ int gx_band_upload(gx_band *b, const uint8_t *s1, const uint8_t *s2) {
     for (int q = 0; q < nl; ++q) off2[q] = b->m + (b->col0[q] - c_lo);
     return gx_plan_upload(b->plan, blob.data(), blob.size(), off1.data(), off2.data());
 }
+GX_GUARD_END
 
-int gx_band_execute(gx_band *b) {
+int gx_band_execute(gx_band *b) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!b) return GX_ERR_ARG;
     if (b->trivial) return GX_OK;
@@ -1400,8 +1459,9 @@ int gx_band_execute(gx_band *b) {
     b->fill_ms = b->plan->fill_ms;
     return rc;
 }
+GX_GUARD_END
 
-int gx_band_score(gx_band *b, int64_t *score, int *valid) {
+int gx_band_score(gx_band *b, int64_t *score, int *valid) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!b || !score || !valid) return GX_ERR_ARG;
     *valid = (b->last == b->n_bands) ? 1 : 0;
@@ -1420,6 +1480,7 @@ int gx_band_score(gx_band *b, int64_t *score, int *valid) {
     *score = sc[nl - 1];
     return GX_OK;
 }
+GX_GUARD_END
 
 double gx_band_stat(const gx_band *b, int what) {
     if (!b) return -1.0;
@@ -1433,7 +1494,7 @@ void gx_band_destroy(gx_band *b) {
     band_free(b);
 }
 
-int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score) {
+int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score) try {
     if (!score || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
     gx_band *b = nullptr;
     int rc = gx_band_create(m, n, n_bands, 0, n_bands, sc, &b);
@@ -1445,11 +1506,12 @@ int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_
     gx_band_destroy(b);
     return rc;
 }
+GX_GUARD_END
 
 // ------------------------------------------------------------------------------------------------
 // small-table visualiser support: display.rs:131-220 prints the path grid and the three score planes
 int gx_debug_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local, int64_t *ins,
-                    int64_t *del, int64_t *sub) {
+                    int64_t *del, int64_t *sub) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!ins || !del || !sub || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
     if (!g_ctx) return GX_ERR_NOT_INIT;
@@ -1494,10 +1556,11 @@ int gx_debug_planes(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n
     pool_free(c, d_planes);
     return rc;
 }
+GX_GUARD_END
 
 int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,
                    const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int flags, gx_result *out,
-                   uint8_t *ops_blob, const uint64_t *ops_off) {
+                   uint8_t *ops_blob, const uint64_t *ops_off) try {
     gx_plan *pl = nullptr;
     int rc = gx_plan_create(len1, len2, n_pairs, sc, is_local, flags, &pl);
     if (rc) return rc;
@@ -1507,13 +1570,15 @@ int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *o
     gx_plan_destroy(pl);
     return rc;
 }
+GX_GUARD_END
 
 int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1, const uint64_t *off2,
-                   const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int64_t *scores) {
+                   const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local, int64_t *scores) try {
     if ((!seq_blob && blob_len) || ((!off1 || !len1 || !off2 || !len2 || !scores) && n_pairs)) return GX_ERR_ARG;
     // large read sets stream through two copy/compute lanes; everything else goes through a plan
-    if (!getenv("GX_NO_STREAM")) {
-        const int rcs = score_batch_streamed(seq_blob, blob_len, off1, len1, off2, len2, n_pairs, sc, is_local, scores);
+    if (!getenv("GX_NO_STREAM")) {   // debug switch, read once per batch call
+        const int rcs = score_batch_streamed(seq_blob, blob_len, off1, len1, off2, len2, n_pairs, sc, is_local, scores,
+                                             getenv("GX_READS32") != nullptr);
         if (rcs != GX_ERR_UNSUPPORTED) return rcs;
     }
     gx_plan *pl = nullptr;
@@ -1525,10 +1590,12 @@ int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len, const uint64_t *o
     gx_plan_destroy(pl);
     return rc;
 }
+GX_GUARD_END
 
 int gx_align_pair(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int is_local, int flags,
-                  gx_result *out, uint8_t *ops, uint64_t ops_cap) {
+                  gx_result *out, uint8_t *ops, uint64_t ops_cap) try {
     if (!out || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
+    if (m > (1ull << 28) || n > (1ull << 28)) return GX_ERR_RANGE;   // before anything is sized from the caller's numbers
     if ((flags & GX_FLAG_TRACEBACK) && (!ops || ops_cap < m + n + 1)) return (!ops) ? GX_ERR_ARG : GX_ERR_OPS_CAP;
     std::vector<uint8_t> blob(m + n);
     if (m) memcpy(blob.data(), s1, m);
@@ -1537,5 +1604,6 @@ int gx_align_pair(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, 
     uint64_t ops_off[2] = {0, ops_cap};
     return gx_align_batch(blob.data(), m + n, &off1, &l1, &off2, &l2, 1, sc, is_local, flags, out, ops, ops_off);
 }
+GX_GUARD_END
 
 }  // extern "C"

@@ -285,8 +285,8 @@ static int launch_reads_gk(const ReadsParams &rp, int sm_count, cudaStream_t st)
 }
 
 // returns -1 if max_len is not supported by this kernel family
-static int launch_reads(const ReadsParams &rp, int max_len, int sm_count, cudaStream_t st) {
-    if (reads16_ok(rp, max_len) && !getenv("GX_READS32")) {
+static int launch_reads(const ReadsParams &rp, int max_len, int sm_count, cudaStream_t st, bool force32 = false) {
+    if (reads16_ok(rp, max_len) && !force32) {
         if (max_len <= 8 * 19) return launch_reads16_gk<8, 19>(rp, sm_count, st);
         if (max_len <= 16 * 20) return launch_reads16_gk<16, 20>(rp, sm_count, st);
         if (max_len <= 32 * 20) return launch_reads16_gk<32, 20>(rp, sm_count, st);

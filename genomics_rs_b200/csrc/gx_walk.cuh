@@ -67,6 +67,14 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 bi = take ? oi : bi;
                 bj = take ? oj : bj;
             }
+            // Table maximum 0: every cell ties, and the last one in row-major order is (m, n) (Iterator::max_by,
+            // algo.rs:311-322).  The tiles cannot be trusted to say so: a padded column right of the table also holds 0
+            // and may have won its tile, which the filter above then dropped together with the tile's real zeros.
+            if (bv <= 0) {
+                bv = 0;
+                bi = (int)m;
+                bj = (int)n;
+            }
         }
         score = bv;
         if (P.have_best) {

@@ -92,6 +92,28 @@ def test_edge_cases(gx, oracle):
                 _same(r, o, oracle, f"{a[:12]!r} {b[:12]!r} {scores} local={is_local}")
 
 
+@pytest.mark.parametrize("k", [0, 4, 8, 16])
+@pytest.mark.parametrize("chain1", [0, 1])
+def test_local_all_zero_table(gx, oracle, k, chain1, monkeypatch):
+    """a local table whose maximum is 0: score 0, start (m, n) -- the LAST cell in row-major order (algo.rs:311-322) --
+    and the run-on walk from there.  Shapes where a padded column right of the table runs through an unmasked batch
+    (n mod 32K in [1, K-1], rows a multiple of the batch) for every register blocking and both recurrence forms."""
+    if k:
+        monkeypatch.setenv("GX_K", str(k))
+    monkeypatch.setenv("GX_CHAIN1", str(chain1))
+    pairs = [(b"A" * 64, b"C"), (b"A" * 4096, b"C"), (b"A" * 8192, b"CC"), (b"A" * 64, b"C" * 3), (b"A" * 128, b"C" * 129),
+             (b"A" * 256, b"C" * 513), (b"A" * 32, b"C" * 5), (b"A" * 31, b"C"), (b"A" * 4160, b"C" * 7), (b"AC" * 40, b"GT" * 33)]
+    for scores in (CONFIG_TOML, TEST_CONFIG):
+        for traceback in (True, False):
+            got = gx.align_batch(pairs, scores, True, traceback=traceback, start_cell=True)
+            for (a, b), r in zip(pairs, got):
+                o = oracle.align_linear(a, b, scores, True)
+                assert r.score == 0 == o.score
+                assert tuple(r.start) == (len(a), len(b)) == tuple(o.start), (len(a), len(b), k, chain1)
+                if traceback:
+                    _same(r, o, oracle, f"m={len(a)} n={len(b)} K={k} chain1={chain1}")
+
+
 @pytest.mark.parametrize("scores", [CONFIG_TOML, TEST_CONFIG, (2, -1, -1, 0), (5, -4, -3, -10), (1, 0, -1, -1), (3, 1, -2, -2)])
 def test_random_small_vs_faithful(gx, oracle, scores):
     rng = np.random.default_rng(hash(scores) & 0xffff)
