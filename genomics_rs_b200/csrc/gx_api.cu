@@ -126,6 +126,7 @@ static void pool_free(Ctx *c, void *p) {
 // Debug / experiment switches.  The environment is read ONCE per plan (gx_plan_create) or per streamed
 // batch call, never on the execute path; -1 = not set.
 struct Tunables {
+    int r = -1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
         fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0;
 };
@@ -136,6 +137,7 @@ static int env_int(const char *name, int dflt) {
 static Tunables read_tunables() {
     Tunables t;
     t.k = env_int("GX_K", -1);
+    t.r = env_int("GX_R", -1);
     t.chain1 = env_int("GX_CHAIN1", -1);
     t.tickets = getenv("GX_TICKETS") ? 1 : -1;
     t.resident = env_int("GX_RESIDENT", -1);
@@ -164,7 +166,7 @@ struct gx_plan {
     gx_scores sc{};
     gx::Tunables tun;                  // debug switches as they were when the plan was created
     int is_local = 0, flags = 0;
-    int K = 8;
+    int K = 8, R = 1;                  // register tile of the fill: K columns x R rows per lane per step
     bool chain1 = false;               // latency-optimised recurrence (gx_fill.cuh, CHAIN1)
     int track = 0;
     bool traceback = false;
@@ -232,27 +234,42 @@ struct gx_band {
 
 namespace gx {
 
-// the fill kernels are instantiated in gx_fill_inst.cu, one translation unit per (K, CHAIN1) so that they build in parallel
-FillKernel pick_fill_4_0(bool prof, bool L, bool C, int track);
-FillKernel pick_fill_4_1(bool prof, bool L, bool C, int track);
-FillKernel pick_fill_8_0(bool prof, bool L, bool C, int track);
-FillKernel pick_fill_8_1(bool prof, bool L, bool C, int track);
-FillKernel pick_fill_16_0(bool prof, bool L, bool C, int track);
-FillKernel pick_fill_16_1(bool prof, bool L, bool C, int track);
-template <int K>
-static FillKernel pick_fill(bool prof, bool chain1, bool L, bool C, int track) {
-    if (K == 4) return chain1 ? pick_fill_4_1(prof, L, C, track) : pick_fill_4_0(prof, L, C, track);
-    if (K == 8) return chain1 ? pick_fill_8_1(prof, L, C, track) : pick_fill_8_0(prof, L, C, track);
-    return chain1 ? pick_fill_16_1(prof, L, C, track) : pick_fill_16_0(prof, L, C, track);
+// (K, R) register tiles the library is built with: K columns x R rows per lane per step (gx_fill.cuh).  R = 1 is the
+// single-row systolic form; R > 1 gives a lone warp instruction-level parallelism across rows and amortises the
+// per-step hand-off over R*K cells.
+#define GX_COMBOS(X) X(4, 1) X(8, 1) X(16, 1) X(4, 4) X(4, 8) X(8, 2) X(8, 4) X(16, 2)
+
+// the fill kernels are instantiated in gx_fill_inst.cu, one translation unit per (K, R, CHAIN1) so that they build in parallel
+#define GX_DECL(K, R)                                                  \
+    FillKernel pick_fill_##K##_##R##_0(bool prof, bool L, bool C, int track); \
+    FillKernel pick_fill_##K##_##R##_1(bool prof, bool L, bool C, int track);
+GX_COMBOS(GX_DECL)
+#undef GX_DECL
+
+static bool combo_ok(int K, int R) {
+#define GX_CHK(k, r) if (K == k && R == r) return true;
+    GX_COMBOS(GX_CHK)
+#undef GX_CHK
+    return false;
 }
 
-template <int K>
+static FillKernel pick_fill(int K, int R, bool prof, bool chain1, bool L, bool C, int track) {
+#define GX_PICK(k, r) if (K == k && R == r) return chain1 ? pick_fill_##k##_##r##_1(prof, L, C, track) : pick_fill_##k##_##r##_0(prof, L, C, track);
+    GX_COMBOS(GX_PICK)
+#undef GX_PICK
+    return nullptr;
+}
+
 static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int track_override = -1) {
     Ctx *c = pl->ctx;
-    void (*kern)(const FillParams) = nullptr;
+    const int K = pl->K;
     const bool L = pl->is_local != 0, C = pl->traceback;
-    kern = (track_override >= 0) ? pick_fill<K>(pl->prof, pl->chain1, L, false, track_override)
-                                 : pick_fill<K>(pl->prof, pl->chain1, L, C, pl->track);
+    FillKernel kern = (track_override >= 0) ? pick_fill(K, pl->R, pl->prof, pl->chain1, L, false, track_override)
+                                            : pick_fill(K, pl->R, pl->prof, pl->chain1, L, C, pl->track);
+    if (!kern) {
+        g_err = "no fill kernel for this (K, R)";
+        return GX_ERR_INTERNAL;
+    }
     // CTA shape: single-warp CTAs while the plan cannot fill half of the warp slots (see gx_common.cuh)
     int wpc = (pl->n_strips * 2 >= (uint64_t)c->sm_count * warps_per_sm(K)) ? WARPS_PER_CTA : 1;
     if (pl->tun.wpc >= 0) wpc = pl->tun.wpc == 1 ? 1 : WARPS_PER_CTA;
@@ -284,11 +301,24 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     return GX_OK;
 }
 
-template <int K>
+typedef void (*WalkKernel)(const WalkParams);
 static int launch_walk(gx_plan *pl, const WalkParams &wp) {
-    const uint32_t smem = wp.traceback ? walk_smem_bytes(K) : 0u;
-    CK(cudaFuncSetAttribute(gx_walk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(K)));
-    gx_walk_kernel<K><<<(unsigned)pl->n_pairs, 32, smem, pl->ctx->stream>>>(wp);
+    WalkKernel kern = nullptr;
+    uint32_t smem_max = 0;
+#define GX_WALK(k, r)                           \
+    if (pl->K == k && pl->R == r) {             \
+        kern = gx_walk_kernel<k, r>;            \
+        smem_max = walk_smem_bytes(k, r);       \
+    }
+    GX_COMBOS(GX_WALK)
+#undef GX_WALK
+    if (!kern) {
+        g_err = "no walk kernel for this (K, R)";
+        return GX_ERR_INTERNAL;
+    }
+    const uint32_t smem = wp.traceback ? smem_max : 0u;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    kern<<<(unsigned)pl->n_pairs, 32, smem, pl->ctx->stream>>>(wp);
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -564,6 +594,8 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
         pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
         if (pl->tun.k == 4 || pl->tun.k == 8 || pl->tun.k == 16) pl->K = pl->tun.k;
+        pl->R = 1;
+        if (pl->tun.r > 0 && combo_ok(pl->K, pl->tun.r)) pl->R = pl->tun.r;
         // latency-optimised recurrence (one more ALU op per cell, 1-op row chain) when warps are too few to hide the
         // classic 3-op chain: measured win below ~1/4 of the resident warps, loss at full occupancy
         {
@@ -575,8 +607,8 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         }
         if (pl->tun.chain1 >= 0) pl->chain1 = pl->tun.chain1 != 0;
     }
-    const int K = pl->K, W = 32 * K;
-    const uint32_t SPC = 64u / (uint32_t)K, BATCH = SPC > 8 ? SPC : 8, CPB = BATCH / SPC;
+    const int K = pl->K, R = pl->R, W = 32 * K;
+    const uint32_t SPC = 64u / (uint32_t)(R * K), BATCH = (uint32_t)geo_batch(K, R), CPB = BATCH / SPC;
     pl->pairs.resize(n_pairs);
     std::vector<TileDesc> tiles;
     std::vector<uint64_t> sbase(n_pairs, 0);
@@ -599,7 +631,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         pd.progress_off = (uint32_t)progress;
         pd.tile_base = (uint32_t)best;
         const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
-        pd.tile_code_bytes = interior ? tile_batches(rows_max, BATCH) * CPB * 32 * 16 : 0;
+        pd.tile_code_bytes = interior ? tile_batches(rows_max, (uint32_t)R, BATCH) * CPB * 32 * 16 : 0;
         pd.col0 = band_col0 ? (uint32_t)band_col0[q] : 0u;
         if (interior) {
             colbuf += (uint64_t)(pd.S - 1) * m;
@@ -1042,7 +1074,7 @@ int gx_plan_execute(gx_plan *pl) try {
     fp.ap = sc.s_match - fp.hg;
     fp.bp = sc.s_mismatch - fp.hg;
     if (pl->n_tiles) {
-        int rc = pl->K == 16 ? launch_fill<16>(pl, fp, 0) : pl->K == 4 ? launch_fill<4>(pl, fp, 0) : launch_fill<8>(pl, fp, 0);
+        int rc = launch_fill(pl, fp, 0);
         if (rc) return rc;
         pl->launches++;
     }
@@ -1070,7 +1102,7 @@ int gx_plan_execute(gx_plan *pl) try {
     wp.have_best = pl->track == 2 ? 1 : 0;
     wp.debug = pl->tun.walk_stats;
     {
-        int rc = pl->K == 16 ? launch_walk<16>(pl, wp) : pl->K == 4 ? launch_walk<4>(pl, wp) : launch_walk<8>(pl, wp);
+        int rc = launch_walk(pl, wp);
         if (rc) return rc;
         pl->launches++;
     }
@@ -1089,7 +1121,7 @@ int gx_plan_execute(gx_plan *pl) try {
             fq.tile_best = pl->d_first;
             fq.stats = nullptr;
             fq.timeline = nullptr;
-            int rc = pl->K == 16 ? launch_fill<16>(pl, fq, 0, 3) : pl->K == 4 ? launch_fill<4>(pl, fq, 0, 3) : launch_fill<8>(pl, fq, 0, 3);
+            int rc = launch_fill(pl, fq, 0, 3);
             if (rc) return rc;
             pl->launches++;
             CK(cudaMemcpyAsync(&abort_word2, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1266,6 +1298,7 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 8: return (double)pl->n_tiles;
         case 9: return (double)pl->kind;
         case 15: return (double)pl->K;
+        case 19: return (double)pl->R;
         case 17: return pl->chain1 ? 1.0 : 0.0;
         case 18: return pl->lcs_ms;
         case 10: case 11: case 12: case 13: case 14: return (double)pl->h_stats[what - 10];

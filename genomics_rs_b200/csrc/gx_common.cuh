@@ -24,9 +24,9 @@ __host__ __device__ constexpr int ctas_per_sm(int K) { return K > 0 ? 2 : 2; }
 __host__ __device__ constexpr int warps_per_sm(int K) { return WARPS_PER_CTA * ctas_per_sm(K); }
 
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
-// the left-boundary in-ring and right-boundary out-ring (32 x 8 B each) and one mbarrier.
+// the left-boundary in-ring and right-boundary out-ring (2 x 32 rows x 8 B each) and one mbarrier.
 constexpr int WARP_SMEM_S1 = PANEL_H + 32;
-constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 256 + 256 + 16;   // offset of the match/mismatch profile
+constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 512 + 512 + 16;   // offset of the match/mismatch profile
 // profile: 4 symbols x (32*K columns) x 4 B = K*512 bytes per warp
 __host__ __device__ constexpr int warp_smem_bytes(int K) { return WARP_SMEM_PROF + K * 512; }
 
@@ -96,7 +96,7 @@ struct WalkParams {
     DevResult *results;
     uint8_t *ops;
     int g, hg, h;
-    int kcols_log2;                  // log2(K) of the fill kernel that wrote the codes
+    int kcols_log2;                  // log2(K) of the fill kernel that wrote the codes (informational; the walk is templated on K, R)
     int is_local, traceback, have_best;
     int debug;                       // GX_WALK_STATS: iterations/reloads/cycles returned in spare result fields
 };

@@ -71,201 +71,276 @@ __device__ __forceinline__ void code_acc(uint32_t &cw, int S, int I, int V, uint
         : "r"(S), "r"(I), "r"(V), "r"(one), "n"(UNIT));
 }
 
-// geometry shared by fill, walk and host: steps are processed in batches of BATCH steps
-template <int K>
+// geometry shared by fill, walk and host.  A lane owns K consecutive columns and works on R consecutive rows per
+// step (an R x K register tile); the 32 lanes of a warp run a systolic skew in units of row blocks: at step t lane l
+// updates row block t-l.  Steps are unrolled one 16-byte code chunk at a time (SPC steps = 64 cells per lane) and
+// the boundary hand-off between strips works in batches of BATCH steps = BATCH*R rows (<= 32: one row per lane).
+template <int K, int R>
 struct Geo {
+    static_assert(R * K <= 64 && (R & (R - 1)) == 0 && (K & (K - 1)) == 0, "R x K cells must fit one 16-byte code chunk");
     static constexpr int W = 32 * K;                       // columns per strip
-    static constexpr int SPC = 64 / K;                     // steps per 16-byte code chunk
-    static constexpr int BATCH = (SPC > 8) ? SPC : 8;      // steps per batch (boundary hand-off granularity)
+    static constexpr int SPC = 64 / (R * K);               // steps per 16-byte code chunk
+    static constexpr int BMIN = (32 / R < 8) ? 32 / R : 8;
+    static constexpr int BATCH = (SPC > BMIN) ? SPC : BMIN;   // steps per batch (boundary hand-off granularity)
     static constexpr int CPB = BATCH / SPC;                // code chunks per batch
+    static constexpr int BR = BATCH * R;                   // rows per batch
     static constexpr int KB = Log2<K>::value;
+    static_assert(BR <= 32, "one boundary row per lane");
 };
-__host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_t batch) { return (rows + 31 + batch - 1) / batch; }
+__host__ __device__ constexpr int geo_batch(int K, int R) {
+    const int spc = 64 / (R * K), bmin = (32 / R < 8) ? 32 / R : 8;
+    return spc > bmin ? spc : bmin;
+}
+// batches of one tile: row blocks (rows rounded up to R) + 31 steps of skew, in batches of `batch` steps
+__host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_t R, uint32_t batch) {
+    return ((rows + R - 1) / R + 31 + batch - 1) / batch;
+}
+
+// lane 0's left boundary comes from the in-ring, every other lane's from its left neighbour's registers: a predicated
+// shared-memory load over the shuffle result instead of LDS + 2 SEL (the selects would sit on the ALU pipe, 2/K per cell)
+__device__ __forceinline__ void lds_over_if(int &x, int &y, const uint2 *p, bool pred) {
+    // (no memory clobber: the load depends on this step's shuffle results, which pins it behind the __syncwarp that
+    // published the in-ring; a clobber would serialise it against every other shared-memory access of the step)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0,%1}, [%2];\n\t}"
+                 : "+r"(x), "+r"(y)
+                 : "r"(smem_u32(p)), "r"((uint32_t)pred));
+}
 
 // One batch of BATCH systolic steps of one warp.
 // THRU (last strip of a column band whose width is not a multiple of the strip): padding columns pass (E,I) of
 // the band's last real column through unchanged, so that lane 31 still publishes the band's right boundary.
 //
 // CHAIN1 selects the latency-optimised form of the recurrence.  The classic form has a 3-instruction dependency
-// per cell along the row (I -> V -> E -> next I, 18 clk with the pipe crossing); CHAIN1 keeps everything in
-// E-space (x + h + g) and takes max(D,S) out of the chain:
+// per cell along the row (I -> V -> E -> next I, 14 clk); CHAIN1 keeps everything in E-space (x + h + g) and takes
+// max(D,S) out of the chain:
 //     Sh = Ediag + sub                (S + h + g: the profile holds the raw match/mismatch scores)
 //     D' = max(D + g, Eup)            Mh = max(D' + (h+g), Sh)
 //     I' = max(I + g, Mh_left)        the only op on the row chain: 1 VIADDMNMX = 4 clk per cell
 //     E  = max(I' + (h+g), Mh)
 // (I' = max(I+g, E_left) = max(I+g, I+h+g, Mh_left) and h <= 0.)  One more ALU-pipe op per cell than the classic
-// form, 4.5x shorter chain: chosen when there are too few strips to hide latency with warps, and for score-only fills.
-template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool CHAIN1, bool THRU = false>
-__device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int &elast, int &ilast, int &vd,
+// form, a much shorter chain: chosen when there are too few strips to hide latency with warps.
+//
+// The R x K cells of a step are emitted anti-diagonal by anti-diagonal: cells of one anti-diagonal are independent,
+// so a single warp has min(R,K)-fold instruction-level parallelism and the dependent chain of a step is R+K-1 cells
+// for R rows (the step latency is what a lone strip, and the ramp of a pair's strip pipeline, run at).
+//
+// Shared-memory fetches are software-pipelined (PIPE): the s1 characters are loaded two steps ahead, the profile rows
+// one step ahead; `c1a` / `subc` carry that state from step to step and batch to batch.
+template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool CHAIN1, bool THRU = false>
+__device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int (&eo)[R], int (&io)[R], int &vd,
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
                                           const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
                                           const uint8_t *prof_lane /* profile base + lane*16 */,
-                                          const uint2 *inr /* left-boundary (E,I) of this batch's steps */, uint2 *outring, uint4 *code_dst, const int t0, const int rows, const int lane,
-                                          const int kvalid, int (&subc)[K] /* PROF: profile row of this batch's first step in, next batch's out */) {
-    using G = Geo<K>;
+                                          const uint2 *inr /* left-boundary (E,I) of this batch's rows */, uint2 *outring, uint4 *code_dst,
+                                          const int t0, const int rows, const int lane, const int kvalid,
+                                          int (&subc)[R * K] /* PIPE+PROF: profile rows of the step about to run */,
+                                          int (&c1a)[R] /* PIPE: s1 characters LOOK-1 steps ahead */) {
+    using G = Geo<K, R>;
     constexpr int KB = G::KB;
-    // K < 16 (registers to spare): the s1 characters of every step of the batch (and of the next batch's first step)
-    // are fetched up front and the profile row of step+1 is fetched while step runs, so that no shared-memory
-    // latency is left on the row chain.  K = 16 lives at the 128-register limit and fetches in-step.
-    constexpr bool PIPE = K < 16;
-    int c1v[G::BATCH + 1];
-    if (PIPE) {
-#pragma unroll
-        for (int st = 0; st <= G::BATCH; ++st) {
-            const int r = t0 + st - lane;
-            if (MASKED || st == G::BATCH) c1v[st] = s1base[min(max(r, 0), rows - 1)];
-            else c1v[st] = s1base[r];
-        }
-    }
-#pragma unroll
+    constexpr bool PIPE = (R * K <= 16) && (K < 16);
+    constexpr int LOOK = PROF ? 2 : 1;      // PIPE: at step s the characters of step s+LOOK are fetched
+    const bool lane0 = lane == 0;
+    // s1 character of tile row r; rows outside the tile are clamped only where they can occur (masked batches) --
+    // an unmasked batch looks at most 2R bytes past the tile's rows, which the staging buffer's slack covers
+    auto s1char = [&](int r) __attribute__((always_inline)) -> int {
+        if (MASKED) return (int)s1base[min(max(r, 0), rows - 1)];
+        return (int)s1base[r];
+    };
+#pragma unroll 1
     for (int ch = 0; ch < G::CPB; ++ch) {
         uint32_t cw[4] = {0u, 0u, 0u, 0u};
         static_for<G::SPC>([&](auto uc) {
             constexpr int uu = decltype(uc)::value;
-            const int step = ch * G::SPC + uu;          // step inside the batch (compile-time after unrolling)
-            const int r = t0 + step - lane;
-            const uint2 bnd = inr[step];
-            int el = __shfl_up_sync(FULL, elast, 1);
-            int il = __shfl_up_sync(FULL, ilast, 1);
-            if (lane == 0) {
-                el = (int)bnd.x;
-                il = (int)bnd.y;
+            const int step = ch * G::SPC + uu;          // step inside the batch
+            const int rb = t0 + step - lane;            // row block of this lane at this step
+            const int r0 = rb * R;
+            // ---- left boundary of the R rows: neighbour lane's registers, lane 0: the in-ring
+            int el[R], il[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                el[rr] = __shfl_up_sync(FULL, eo[rr], 1);
+                il[rr] = __shfl_up_sync(FULL, io[rr], 1);
+                lds_over_if(el[rr], il[rr], inr + step * R + rr, lane0);
             }
-            bool active = true;
-            if (MASKED) active = (r >= 0) && (r < rows);
-            int c1 = 0;
-            if (PIPE) c1 = c1v[step];
-            else c1 = MASKED ? s1base[min(max(r, 0), rows - 1)] : s1base[r];
-            int sub[K];
-            if (PROF) {
-                // profile layout [sym][k/4][lane][k%4] ints -> K/4 conflict-free LDS.128 per row
-                if (PIPE) {
-                    // this step's profile row was fetched one step ago (subc); fetch the next step's now
+            bool act[R];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) sub[k] = subc[k];
-                }
-                const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + (PIPE ? c1v[step + 1] : c1) * (K * 128));
+            for (int rr = 0; rr < R; ++rr) act[rr] = MASKED ? ((r0 + rr >= 0) && (r0 + rr < rows)) : true;
+            // ---- match/mismatch scores of the R x K cells
+            int sub[R * K];
+            if (PIPE) {
+                int c1[R];   // characters of THIS step (compare path only)
+                if (PROF) {
 #pragma unroll
-                for (int q = 0; q < K / 4; ++q) {
-                    const int4 v = pp[q * 32];
-                    if (PIPE) {
-                        subc[4 * q + 0] = v.x;
-                        subc[4 * q + 1] = v.y;
-                        subc[4 * q + 2] = v.z;
-                        subc[4 * q + 3] = v.w;
-                    } else {
-                        sub[4 * q + 0] = v.x;
-                        sub[4 * q + 1] = v.y;
-                        sub[4 * q + 2] = v.z;
-                        sub[4 * q + 3] = v.w;
+                    for (int x = 0; x < R * K; ++x) sub[x] = subc[x];
+                    // profile rows of the next step (characters fetched one step ago) ...
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1a[rr] * (K * 128));
+#pragma unroll
+                        for (int q = 0; q < K / 4; ++q) {
+                            const int4 v = pp[q * 32];
+                            subc[rr * K + 4 * q + 0] = v.x;
+                            subc[rr * K + 4 * q + 1] = v.y;
+                            subc[rr * K + 4 * q + 2] = v.z;
+                            subc[rr * K + 4 * q + 3] = v.w;
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) c1[rr] = c1a[rr];
+                }
+                // ... and the characters LOOK steps ahead
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) c1a[rr] = s1char(r0 + LOOK * R + rr);
+                if (!PROF) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sub[rr * K + k] = (c1[rr] == c2[k]) ? ap : bp;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < K; ++k) sub[k] = (c1 == c2[k]) ? ap : bp;
+                for (int rr = 0; rr < R; ++rr) {
+                    const int c1 = s1char(r0 + rr);
+                    if (PROF) {
+                        // profile layout [sym][k/4][lane][k%4] ints -> K/4 conflict-free LDS.128 per row
+                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
+#pragma unroll
+                        for (int q = 0; q < K / 4; ++q) {
+                            const int4 v = pp[q * 32];
+                            sub[rr * K + 4 * q + 0] = v.x;
+                            sub[rr * K + 4 * q + 1] = v.y;
+                            sub[rr * K + 4 * q + 2] = v.z;
+                            sub[rr * K + 4 * q + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sub[rr * K + k] = (c1 == c2[k]) ? ap : bp;
+                    }
+                }
             }
-            int e = el, irun = il, ed = vd;
-            int rowbest = (CHAIN1 || TRACK == 3) ? INT32_MIN : -1;
-            int mh = el;   // CHAIN1: "max(D,S) of the cell to the left" -- for the lane's first column that is E_left itself
-            static_for<K>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                int In, Dn, En, Skey, Ikey, Vkey;   // S/I/V keys: equal keys decide the direction code; Vkey orders the local maximum
-                if (CHAIN1) {
-                    In = LOCAL ? __viaddmax_s32_relu(irun, g, mh) : __viaddmax_s32(irun, g, mh);
-                    Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                    const int Sh = ed + sub[k];
-                    const int Mh = __viaddmax_s32(Dn, hg, Sh);
-                    En = __viaddmax_s32(In, hg, Mh);   // local: I' >= 0 keeps E >= h+g, i.e. V >= 0
-                    if (THRU) mh = (k < kvalid) ? Mh : mh;
-                    else mh = Mh;
-                    Skey = Sh;
-                    Ikey = CODES ? In + hg : 0;
-                    Vkey = En;     // E-space: same order, same equalities
-                } else {
-                    In = LOCAL ? __viaddmax_s32_relu(irun, g, e) : __viaddmax_s32(irun, g, e);
-                    Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                    const int Sn = ed + sub[k];
-                    const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
-                    En = Vn + hg;
-                    Skey = Sn;
-                    Ikey = In;
-                    Vkey = Vn;
-                }
-                if (CODES) {
-                    constexpr int bitpos = uu * 2 * K + 2 * k;
-                    code_acc<(1u << (bitpos & 31))>(cw[bitpos >> 5], Skey, Ikey, Vkey, one);
-                }
-                ed = eu[k];
-                if (MASKED) {
-                    eu[k] = active ? En : eu[k];
-                    du[k] = active ? Dn : du[k];
-                } else {
-                    eu[k] = En;
-                    du[k] = Dn;
-                }
-                if (THRU) {
-                    e = (k < kvalid) ? En : e;
-                    irun = (k < kvalid) ? In : irun;
-                } else {
-                    e = En;
-                    irun = In;
-                }
-                if (TRACK == 2) {
-                    int key = (Vkey << KB) | k;
-                    if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
-                    rowbest = max(rowbest, key);
-                } else if (TRACK == 1) {
-                    int key = Vkey;
-                    if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
-                    rowbest = max(rowbest, key);
-                } else if (TRACK == 3) {
-                    // first maximum in row-major order (alignment_table's max_cell, algo.rs:258-262, strict `<`):
-                    // inside the row the key's low bits prefer the SMALLER column
-                    int key = (Vkey << KB) | (K - 1 - k);
-                    if (PAD) key = (k < kvalid) ? key : INT32_MIN;
-                    rowbest = max(rowbest, key);
-                }
+            // ---- the R x K cells, anti-diagonal by anti-diagonal
+            int e_[R], i_[R], ed_[R], mh_[R], rowbest[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                e_[rr] = el[rr];
+                i_[rr] = il[rr];
+                ed_[rr] = (rr == 0) ? vd : el[rr > 0 ? rr - 1 : 0];
+                mh_[rr] = el[rr];   // CHAIN1: "max(D,S) of the cell to the left" -- for the lane's first column that is E_left itself
+                rowbest[rr] = (CHAIN1 || TRACK == 3) ? INT32_MIN : -1;
+            }
+            static_for<R + K - 1>([&](auto dc) {
+                constexpr int d = decltype(dc)::value;
+                static_for<R>([&](auto rc) {
+                    constexpr int rr = decltype(rc)::value;
+                    constexpr int k = d - rr;
+                    if constexpr (k >= 0 && k < K) {
+                        int In, Dn, En, Skey, Ikey, Vkey;   // S/I/V keys: equal keys decide the direction code; Vkey orders the local maximum
+                        if (CHAIN1) {
+                            In = LOCAL ? __viaddmax_s32_relu(i_[rr], g, mh_[rr]) : __viaddmax_s32(i_[rr], g, mh_[rr]);
+                            Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
+                            const int Sh = ed_[rr] + sub[rr * K + k];
+                            const int Mh = __viaddmax_s32(Dn, hg, Sh);
+                            En = __viaddmax_s32(In, hg, Mh);   // local: I' >= 0 keeps E >= h+g, i.e. V >= 0
+                            if (THRU) mh_[rr] = (k < kvalid) ? Mh : mh_[rr];
+                            else mh_[rr] = Mh;
+                            Skey = Sh;
+                            Ikey = CODES ? In + hg : 0;
+                            Vkey = En;     // E-space: same order, same equalities
+                        } else {
+                            In = LOCAL ? __viaddmax_s32_relu(i_[rr], g, e_[rr]) : __viaddmax_s32(i_[rr], g, e_[rr]);
+                            Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
+                            const int Sn = ed_[rr] + sub[rr * K + k];
+                            const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
+                            En = Vn + hg;
+                            Skey = Sn;
+                            Ikey = In;
+                            Vkey = Vn;
+                        }
+                        if (CODES) {
+                            constexpr int bitpos = ((uu * R + rr) * K + k) * 2;
+                            code_acc<(1u << (bitpos & 31))>(cw[bitpos >> 5], Skey, Ikey, Vkey, one);
+                        }
+                        ed_[rr] = eu[k];
+                        if (MASKED) {
+                            eu[k] = act[rr] ? En : eu[k];
+                            du[k] = act[rr] ? Dn : du[k];
+                        } else {
+                            eu[k] = En;
+                            du[k] = Dn;
+                        }
+                        if (THRU) {
+                            e_[rr] = (k < kvalid) ? En : e_[rr];
+                            i_[rr] = (k < kvalid) ? In : i_[rr];
+                        } else {
+                            e_[rr] = En;
+                            i_[rr] = In;
+                        }
+                        if (TRACK == 2) {
+                            int key = (Vkey << KB) | k;
+                            if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
+                            rowbest[rr] = max(rowbest[rr], key);
+                        } else if (TRACK == 1) {
+                            int key = Vkey;
+                            if (PAD) key = (k < kvalid) ? key : (CHAIN1 ? INT32_MIN : -1);
+                            rowbest[rr] = max(rowbest[rr], key);
+                        } else if (TRACK == 3) {
+                            // first maximum in row-major order (alignment_table's max_cell, algo.rs:258-262, strict `<`):
+                            // inside the row the key's low bits prefer the SMALLER column
+                            int key = (Vkey << KB) | (K - 1 - k);
+                            if (PAD) key = (k < kvalid) ? key : INT32_MIN;
+                            rowbest[rr] = max(rowbest[rr], key);
+                        }
+                    }
+                });
             });
-            if (MASKED) vd = active ? el : vd;
-            else vd = el;
-            elast = e;
-            ilast = irun;
-            if (TRACK == 2) {
-                // last maximum in row-major order wins (Iterator::max_by, algo.rs:311-322): a later row
-                // replaces an equal value; inside the row the key's low bits prefer the larger column.
-                const bool upd = active && ((rowbest | (K - 1)) >= best);
-                best = upd ? rowbest : best;
-                best_r = upd ? r : best_r;
-            } else if (TRACK == 1) {
-                best = active ? max(best, rowbest) : best;
-            } else if (TRACK == 3) {
-                // only a strictly larger value replaces the running first maximum (rows arrive in increasing order)
-                const bool upd = active && ((rowbest | (K - 1)) > (best | (K - 1)));
-                best = upd ? rowbest : best;
-                best_r = upd ? r : best_r;
+            if (MASKED) vd = act[0] ? el[R - 1] : vd;
+            else vd = el[R - 1];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                eo[rr] = e_[rr];
+                io[rr] = i_[rr];
+                if (TRACK == 2) {
+                    // last maximum in row-major order wins (Iterator::max_by, algo.rs:311-322): a later row
+                    // replaces an equal value; inside the row the key's low bits prefer the larger column.
+                    const bool upd = act[rr] && ((rowbest[rr] | (K - 1)) >= best);
+                    best = upd ? rowbest[rr] : best;
+                    best_r = upd ? r0 + rr : best_r;
+                } else if (TRACK == 1) {
+                    best = act[rr] ? max(best, rowbest[rr]) : best;
+                } else if (TRACK == 3) {
+                    // only a strictly larger value replaces the running first maximum (rows arrive in increasing order)
+                    const bool upd = act[rr] && ((rowbest[rr] | (K - 1)) > (best | (K - 1)));
+                    best = upd ? rowbest[rr] : best;
+                    best_r = upd ? r0 + rr : best_r;
+                }
+                if (lane == 31 && act[rr]) outring[step * R + rr] = make_uint2((uint32_t)e_[rr], (uint32_t)i_[rr]);   // row R*(t0+step-31)+rr
             }
-            if (lane == 31 && active) outring[step] = make_uint2((uint32_t)e, (uint32_t)irun);   // row t0+step-31
         });
         if (CODES) st_cs_uint4(code_dst + ch * 32, make_uint4(cw[0], cw[1], cw[2], cw[3]));
     }
 }
 
-template <int K, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
+template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
 __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(const FillParams P) {
-    using G = Geo<K>;
+    using G = Geo<K, R>;
     constexpr int W = G::W;
-    constexpr int B = G::BATCH;
+    constexpr int B = G::BATCH;     // steps per batch
+    constexpr int BR = G::BR;       // rows per batch
     constexpr int KB = G::KB;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     uint8_t *wsm = smem + wib * warp_smem_bytes(K);
     uint8_t *s1buf = wsm;
-    uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);
-    uint2 *outring = inring + 32;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 32);
+    uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);   // 2 x BR entries (double-buffered by batch)
+    uint2 *outring = inring + 64;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 64);
     uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints = K*512 bytes
 
+    // the s1 staging buffer starts out as valid symbols: unmasked batches prefetch up to 2R bytes past the rows the
+    // TMA copy delivered (stale bytes of an earlier tile, or these zeros -- any symbol 0..3 indexes a real profile row)
+    for (int x = lane; x < WARP_SMEM_S1 / 16; x += 32) reinterpret_cast<uint4 *>(s1buf)[x] = make_uint4(0u, 0u, 0u, 0u);
     if (lane == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
@@ -430,18 +505,20 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         dead = __any_sync(FULL, dead);
         if (dead) break;
 
-        int elast = 0, ilast = 0;
+        int eo[R], io[R];   // this lane's right edge (E, I) of the R rows of its last step: what the next lane shuffles in
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) eo[rr] = io[rr] = 0;
         int best = (CHAIN1 || TRACK == 3) ? INT32_MIN : -1, best_r = 0;
-        const uint32_t nbat = tile_batches((uint32_t)rows, B);
+        const uint32_t nbat = tile_batches((uint32_t)rows, R, B);
         uint4 *code_base = nullptr;
         if (CODES)
             code_base = reinterpret_cast<uint4 *>(P.codes + pd->codes_off + (uint64_t)(p * S + s) * pd->tile_code_bytes) + lane;
 
-        // ---- left boundary prefetch (LL protocol): lanes 0..B-1 fetch the entries of local rows B*bt + lane
+        // ---- left boundary prefetch (LL protocol): lanes 0..BR-1 fetch the entries of local rows BR*bt + lane
         unsigned long long nxt = 0;
         auto issue = [&](uint32_t bt) __attribute__((always_inline)) {
-            const int r = (int)(B * bt) + lane;
-            if (has_left && lane < B && r < rows) nxt = ld_bnd(cb_in + r);
+            const int r = (int)(BR * bt) + lane;
+            if (has_left && lane < BR && r < rows) nxt = ld_bnd(cb_in + r);
         };
         if (has_left && P.start_lead > 0) {
             // slack: do not start before the left neighbour is start_lead rows into this panel
@@ -480,20 +557,34 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         const uint8_t *s1base = s1buf + delta;
         const uint8_t *prof_lane = prof + lane * 16;
         __syncwarp();   // profile stores visible to the whole warp
-        int subc[K];    // PROF: profile row of the next step to run (software-pipelined shared-memory fetch)
-        if (PROF) {
-            const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + s1base[0] * (K * 128));
+        // software-pipelined shared-memory fetches (run_batch, PIPE): profile rows of step 0, characters LOOK-1 steps ahead
+        int subc[R * K], c1a[R];
+        {
+            constexpr bool PIPE = (R * K <= 16) && (K < 16);
+            constexpr int LOOK = PROF ? 2 : 1;
 #pragma unroll
-            for (int q = 0; q < K / 4; ++q) {
-                const int4 v = pp[q * 32];
-                subc[4 * q + 0] = v.x;
-                subc[4 * q + 1] = v.y;
-                subc[4 * q + 2] = v.z;
-                subc[4 * q + 3] = v.w;
+            for (int x = 0; x < R * K; ++x) subc[x] = 0;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) c1a[rr] = 0;
+            if (PIPE) {
+                if (PROF) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int c1 = s1base[min(max(-lane * R + rr, 0), rows - 1)];
+                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
+#pragma unroll
+                        for (int q = 0; q < K / 4; ++q) {
+                            const int4 v = pp[q * 32];
+                            subc[rr * K + 4 * q + 0] = v.x;
+                            subc[rr * K + 4 * q + 1] = v.y;
+                            subc[rr * K + 4 * q + 2] = v.z;
+                            subc[rr * K + 4 * q + 3] = v.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) c1a[rr] = s1base[min(max((LOOK - 1 - lane) * R + rr, 0), rows - 1)];
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) subc[k] = 0;
         }
 
         // ---- batch loop.  The hand-off rings are double-buffered (the global load of batch bt+2's left boundary is in
@@ -501,9 +592,9 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         //      then settle the in-ring of the next batch (post() below).
         // settle(b): lanes 0..B-1 turn the prefetched word of local row B*b+lane into an in-ring entry.
         // The common case (data already there) is branch-free apart from one vote.
-        const bool lane_b = lane < B;
+        const bool lane_b = lane < BR;
         auto settle = [&](uint32_t b) __attribute__((always_inline)) -> bool {
-            const int rb = (int)(B * b) + lane;
+            const int rb = (int)(BR * b) + lane;
             const bool need = has_left && lane_b && (rb < rows);
             bool ok = !need || ((((uint32_t)(nxt >> 32)) & 1u) == parity);
             if (!__all_sync(FULL, ok)) {
@@ -528,7 +619,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             uint2 cur;
             cur.x = has_left ? (uint32_t)nxt : (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
             cur.y = has_left ? (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1) : (uint32_t)NEG32;
-            if (lane_b) inring[(b & 1u) * B + lane] = cur;
+            if (lane_b) inring[(b & 1u) * BR + lane] = cur;
             return true;
         };
         if (!settle(0)) dead = true;
@@ -550,8 +641,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         // and the rows finished in batch bt are published before anything else can block.
         const bool has_out = cb_out != nullptr;
         auto post = [&](uint32_t bt, uint2 *outr) __attribute__((always_inline)) -> bool {
-            // rows lane 31 finished in this batch: t0-31 .. t0+B-32
-            const int ro = (int)(B * bt) - 31 + lane;
+            // rows lane 31 finished in this batch: row blocks t0-31 .. t0+B-32
+            const int ro = ((int)(B * bt) - 31) * R + lane;
             const bool take = has_out && lane_b && ro >= 0 && ro < rows;
             __syncwarp();                                    // out-ring stores of this batch -> visible
             if (take) pub = lds_volatile_uint2(outr + lane);
@@ -567,8 +658,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         };
         // batches [0, nb_head) and [nb_body, nbat) touch rows outside the tile (skew) and run the masked steps;
         // the body runs unmasked steps with straight-line glue.
-        const uint32_t nb_head = (30 + B) / B;                       // first batch with t0 >= 31
-        const uint32_t nb_body = max(nb_head, (uint32_t)rows / B);   // first batch with t0 + B - 1 > rows - 1
+        const uint32_t nb_head = (30 + B) / B;                              // first batch with t0 >= 31
+        const uint32_t nb_body = max(nb_head, ((uint32_t)rows / R) / B);    // first batch that reaches past the last full row block
         bool thru = false;
         if constexpr (!LOCAL && !CODES && TRACK == 0) thru = right_band && has_pad;
         // phase 0: masked head batches (all batches of a THRU tile), then the unmasked body; phase 1: masked tail.
@@ -578,18 +669,18 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         for (int ph = 0; ph < 2 && !dead; ++ph) {
             const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
             for (; bt < m_end && !dead; ++bt) {
-                uint2 *outr = outring + (bt & 1u) * B;
+                uint2 *outr = outring + (bt & 1u) * BR;
                 uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
                 if constexpr (!LOCAL && !CODES && TRACK == 0) {
                     if (thru)
-                        run_batch<K, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                                           one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
-                                                                                           (int)(B * bt), rows, lane, kvalid, subc);
+                        run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                           one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                           (int)(B * bt), rows, lane, kvalid, subc, c1a);
                 }
                 if (!thru)
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                                        one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
-                                                                                        (int)(B * bt), rows, lane, kvalid, subc);
+                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                        one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                        (int)(B * bt), rows, lane, kvalid, subc, c1a);
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
@@ -598,20 +689,20 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             // cell it derives from, so the plain body is exact -- the tile reductions ignore winners with j > n.
             if ((TRACK != 0) && has_pad && P.pad_keys != 0u) {
                 for (; bt < nb_body && !dead; ++bt) {
-                    uint2 *outr = outring + (bt & 1u) * B;
+                    uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                                 one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
-                                                                                 (int)(B * bt), rows, lane, kvalid, subc);
+                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                 one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                 (int)(B * bt), rows, lane, kvalid, subc, c1a);
                     if (!post(bt, outr)) dead = true;
                 }
             } else {
                 for (; bt < nb_body && !dead; ++bt) {
-                    uint2 *outr = outring + (bt & 1u) * B;
+                    uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
-                    run_batch<K, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, elast, ilast, vd, best, best_r, g, hg, ap, bp,
-                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * B, outr, cdst,
-                                                                                  (int)(B * bt), rows, lane, kvalid, subc);
+                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                  (int)(B * bt), rows, lane, kvalid, subc, c1a);
                     if (!post(bt, outr)) dead = true;
                 }
             }

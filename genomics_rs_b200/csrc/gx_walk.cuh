@@ -19,13 +19,15 @@
 
 namespace gx {
 
-// dynamic shared memory of one walk warp: two window buffers (codes + label characters)
-__host__ __device__ constexpr uint32_t walk_buf_bytes(int K) {
-    return (uint32_t)(((256 + 32 + 64 / K - 1) / (64 / K) + 1) * 32 * 16 + (256 + 32) + (32 * K + 32) + 15) & ~15u;
+// dynamic shared memory of one walk warp: two window buffers (codes + label characters).
+// A window is 256 rows of one strip = 256/R (+1) row blocks + 31 steps of lane skew, 64/(R*K) steps per code chunk.
+__host__ __device__ constexpr uint32_t walk_chunks(int K, int R) { return (uint32_t)((256 / R + 1 + 31 + 64 / (R * K) - 1) / (64 / (R * K)) + 1); }
+__host__ __device__ constexpr uint32_t walk_buf_bytes(int K, int R) {
+    return (uint32_t)(walk_chunks(K, R) * 32 * 16 + (256 + 32) + (32 * K + 32) + 15) & ~15u;
 }
-__host__ __device__ constexpr uint32_t walk_smem_bytes(int K) { return 2 * walk_buf_bytes(K); }
+__host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R) { return 2 * walk_buf_bytes(K, R); }
 
-template <int K>
+template <int K, int R>
 __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     const uint32_t q = blockIdx.x;
     if (q >= P.n_pairs) return;
@@ -100,16 +102,16 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     res.fill_ms = res.walk_ms = 0.0;
 
     if (P.traceback) {
-        using G = Geo<K>;
+        using G = Geo<K, R>;
         constexpr int SPC = G::SPC;
         constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
-        constexpr int NCH = (WR + 32 + SPC - 1) / SPC + 1;    // code chunks per fill-lane in a window
+        constexpr int NCH = (int)walk_chunks(K, R);           // code chunks per fill-lane in a window
         // Two window buffers in dynamic shared memory: the walk reads buffer `cb`; the other one receives the window the
         // walk will probably need next (prefetched with cp.async while the walk runs).  Per buffer: code chunks
         // [chunk][fill-lane] + the label characters of the window: is_match(i,j) reads s1[i] and s2[j] (0-based: the
         // characters AFTER the cell's own, algo.rs:354), i.e. s1[i0w+1 ..] for the rows and s2[j0w+1 ..] for the columns.
         extern __shared__ __align__(16) uint8_t walk_smem[];
-        constexpr uint32_t BUF_BYTES = walk_buf_bytes(K);
+        constexpr uint32_t BUF_BYTES = walk_buf_bytes(K, R);
         uint32_t cb = 0;
         const uint4 *win = reinterpret_cast<const uint4 *>(walk_smem);
         const uint8_t *s1w = walk_smem + NCH * 32 * 16;
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
             const uint32_t l = (jj % G::W) / K, k = jj % K;
             const uint32_t r = ii & (PANEL_H - 1);
             const bool inwin = ((ii >> PANEL_H_LOG2) == wp) & ((jj / G::W) == ws) & ((r - wr0) <= (wr1 - wr0));
-            const uint32_t t = r + l;
-            const uint32_t bitpos = (t % SPC) * 2 * K + 2 * k;
+            const uint32_t t = r / R + l;                         // the step at which fill-lane l worked on this row's block
+            const uint32_t bitpos = (((t % SPC) * R + r % R) * K + k) * 2;
             const uint32_t widx = inwin ? (((t / SPC - wc0) * 32 + l) * 4 + (bitpos >> 5)) : 0u;
             const uint32_t word = reinterpret_cast<const uint32_t *>(win)[widx];
             uint32_t code = inwin ? ((word >> (bitpos & 31u)) & 3u) : 7u;
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                     const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
                     // copies of `nch` chunks of tile (p, s) starting at chunk c0w into buffer b (asynchronous)
                     auto issue_codes = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) {
-                        const uint32_t c0w = r0 / SPC;
-                        const uint32_t nch = (r1 + 31) / SPC - c0w + 1;   // <= NCH
+                        const uint32_t c0w = (r0 / R) / SPC;
+                        const uint32_t nch = (r1 / R + 31) / SPC - c0w + 1;   // <= NCH
                         const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
                                                                              (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
                                             (size_t)c0w * 32 + lane;
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                         issue_codes(cb, wp, ws, wr0, wr1);
                     }
                     np = 0xffffffffu;
-                    wc0 = wr0 / SPC;
+                    wc0 = (wr0 / R) / SPC;
                     uint8_t *base = walk_smem + cb * BUF_BYTES;
                     win = reinterpret_cast<const uint4 *>(base);
                     uint8_t *s1wm = base + NCH * 32 * 16, *s2wm = s1wm + (WR + 32);

@@ -12,7 +12,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import CONFIG_TOML, GOLDEN, TEST_CONFIG, random_pair
+from conftest import CONFIG_TOML, GOLDEN, KR_COMBOS, TEST_CONFIG, force_kr, random_pair
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -133,11 +133,11 @@ def gx():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [4, 8, 16])
-def test_banded_local_vs_oracle(gx, oracle, k, monkeypatch):
+@pytest.mark.parametrize("k,r", KR_COMBOS)
+def test_banded_local_vs_oracle(gx, oracle, k, r, monkeypatch):
     """N bands emulated on one GPU (one kernel over all bands' strips) against the oracle: sizes that put band
     edges inside strips, on panel boundaries and next to the table edge"""
-    monkeypatch.setenv("GX_K", str(k))
+    force_kr(monkeypatch, k, r)
     rng = np.random.default_rng(21)
     cases = [(1, 1, 1), (5, 9, 3), (300, 8, 8), (700, 900, 2), (4096, 1000, 3), (4097, 1025, 5), (9000, 5000, 8),
              (100, 40000, 4), (12000, 33000, 8), (20000, 4096 * 8, 8), (8200, 70000, 16)]

@@ -3,7 +3,7 @@ oracle and the committed golden vectors.  Integer work: every comparison is bit-
 import numpy as np
 import pytest
 
-from conftest import CONFIG_TOML, TEST_CONFIG, random_pair, read_fasta_gz
+from conftest import CONFIG_TOML, KR_COMBOS, TEST_CONFIG, force_kr, random_pair, read_fasta_gz
 
 pytestmark = pytest.mark.gpu
 
@@ -92,14 +92,14 @@ def test_edge_cases(gx, oracle):
                 _same(r, o, oracle, f"{a[:12]!r} {b[:12]!r} {scores} local={is_local}")
 
 
-@pytest.mark.parametrize("k", [0, 4, 8, 16])
+@pytest.mark.parametrize("k,r", [(0, 0)] + KR_COMBOS)
 @pytest.mark.parametrize("chain1", [0, 1])
-def test_local_all_zero_table(gx, oracle, k, chain1, monkeypatch):
+def test_local_all_zero_table(gx, oracle, k, r, chain1, monkeypatch):
     """a local table whose maximum is 0: score 0, start (m, n) -- the LAST cell in row-major order (algo.rs:311-322) --
     and the run-on walk from there.  Shapes where a padded column right of the table runs through an unmasked batch
     (n mod 32K in [1, K-1], rows a multiple of the batch) for every register blocking and both recurrence forms."""
     if k:
-        monkeypatch.setenv("GX_K", str(k))
+        force_kr(monkeypatch, k, r)
     monkeypatch.setenv("GX_CHAIN1", str(chain1))
     pairs = [(b"A" * 64, b"C"), (b"A" * 4096, b"C"), (b"A" * 8192, b"CC"), (b"A" * 64, b"C" * 3), (b"A" * 128, b"C" * 129),
              (b"A" * 256, b"C" * 513), (b"A" * 32, b"C" * 5), (b"A" * 31, b"C"), (b"A" * 4160, b"C" * 7), (b"AC" * 40, b"GT" * 33)]
@@ -128,21 +128,27 @@ def test_random_small_vs_faithful(gx, oracle, scores):
             _same(r, o, oracle, f"m={len(a)} n={len(b)} {scores} local={is_local}")
 
 
-@pytest.mark.parametrize("k", [4, 8, 16])
-def test_random_medium_ragged_vs_linear(gx, oracle, k, monkeypatch):
-    """sizes that cross strip (32*K columns), batch (8 rows) and panel (4096 rows) boundaries, for every
-    register-blocking factor K the library can pick (GX_K forces it)"""
-    monkeypatch.setenv("GX_K", str(k))
+_RAGGED_ORACLE = {}
+
+
+@pytest.mark.parametrize("chain1", [0, 1])
+@pytest.mark.parametrize("k,r", KR_COMBOS)
+def test_random_medium_ragged_vs_linear(gx, oracle, k, r, chain1, monkeypatch):
+    """sizes that cross strip (32*K columns), batch (up to 32 rows) and panel (4096 rows) boundaries, for every
+    K x R register tile the library can pick (GX_K / GX_R force it) and both forms of the recurrence"""
+    force_kr(monkeypatch, k, r)
+    monkeypatch.setenv("GX_CHAIN1", str(chain1))
     rng = np.random.default_rng(11)
     dims = [(255, 256), (256, 257), (257, 255), (31, 600), (33, 1025), (1000, 31), (513, 513), (4095, 300), (4096, 300),
             (4097, 300), (4200, 520), (300, 4200), (8193, 770), (1, 3000), (3000, 1), (127, 129), (129, 127), (511, 512),
-            (64, 1030)]
-    pairs = [random_pair(rng, m, n, similar=(k % 3 != 0)) for k, (m, n) in enumerate(dims)]
+            (64, 1030), (2, 70), (3, 513), (5, 5), (7, 260), (4094, 140), (4099, 130), (8190, 40), (8197, 33), (33, 4100)]
+    pairs = [random_pair(rng, m, n, similar=(x % 3 != 0)) for x, (m, n) in enumerate(dims)]
     for is_local in (False, True):
         got = gx.align_batch(pairs, CONFIG_TOML, is_local)
-        for (a, b), r in zip(pairs, got):
-            o = oracle.align_linear(a, b, CONFIG_TOML, is_local)
-            _same(r, o, oracle, f"m={len(a)} n={len(b)} local={is_local}")
+        for x, ((a, b), res) in enumerate(zip(pairs, got)):
+            if (x, is_local) not in _RAGGED_ORACLE:     # the same seeded pairs for every (K, R, form): one oracle run each
+                _RAGGED_ORACLE[(x, is_local)] = oracle.align_linear(a, b, CONFIG_TOML, is_local)
+            _same(res, _RAGGED_ORACLE[(x, is_local)], oracle, f"m={len(a)} n={len(b)} local={is_local} K={k} R={r} chain1={chain1}")
 
 
 def test_score_only_and_start_cell(gx, oracle):
@@ -158,10 +164,10 @@ def test_score_only_and_start_cell(gx, oracle):
             assert r.score == oracle.score_linear(a, b, CONFIG_TOML, is_local)[0]
 
 
-@pytest.mark.parametrize("k", [4, 16])
+@pytest.mark.parametrize("k,r", KR_COMBOS)
 @pytest.mark.parametrize("is_local", [False, True])
-def test_brca2_other_blockings(gx, oracle, goldens, k, is_local, monkeypatch):
-    monkeypatch.setenv("GX_K", str(k))
+def test_brca2_other_blockings(gx, oracle, goldens, k, r, is_local, monkeypatch):
+    force_kr(monkeypatch, k, r)
     g = next(p for p in goldens["pairs"] if p["fixture"] == "Human-Mouse-BRCA2-cds" and p["is_local"] == is_local)
     s = read_fasta_gz("Human-Mouse-BRCA2-cds")
     a = gx.align_batch([(s[0][1], s[1][1])], CONFIG_TOML, is_local)[0]

@@ -17,6 +17,10 @@ __global__ void __launch_bounds__(256) probe(int *sink, long long *cycles, int s
 #pragma unroll
     for (int c = 0; c < CH; ++c) f[c] = (float)v[c];
     const float fa = (float)seed * 0.5f, fb = (float)seed;
+    unsigned f_acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) f_acc[c] = 0u;
+    const unsigned one = (unsigned)(seed > 0);
     __syncthreads();
     const long long t0 = clock64();
 #pragma unroll 1
@@ -38,12 +42,34 @@ __global__ void __launch_bounds__(256) probe(int *sink, long long *cycles, int s
             if (OP == 12) { v[c] = (v[c] == w[c]) ? g : hg; }                                                 // ISETP + SEL
             if (OP == 13) { v[c] = __viaddmax_s32(v[c], -1, w[c]); w[c] = __viaddmax_s32(w[c], -1, v[c]); }   // 2 DPX dependent pair
             if (OP == 14) asm volatile("vadd.s32.s32.s32 %0, %0, %1;" : "+r"(v[c]) : "r"(w[c]));
+            if (OP == 15) v[c] = __dp4a(w[c], g, v[c]);                                                       // IDP.4A r,r,r
+            if (OP == 16) { v[c] = __dp4a(w[c], g, v[c]); w[c] = __viaddmax_s32(w[c], -1, hg); }             // IDP.4A + DPX pair
+            if (OP == 17) { v[c] = __dp4a(w[c], g, v[c]); asm volatile("mad.lo.s32 %0, %0, 3, %1;" : "+r"(w[c]) : "r"(g)); }   // IDP.4A + IMAD pair
+            if (OP == 18) {   // the score-only cell mix: 2 VIADDMNMX + VIMNMX3 on the ALU pipe, IDP.4A + IMAD.IADD on the FMA pipe
+                const int In = __viaddmax_s32(v[c], g, w[c]);
+                const int Sn = __dp4a(w[c], hg, v[c]);
+                const int Dn = __viaddmax_s32(w[c], g, In);
+                const int Vn = __vimax3_s32(In, Dn, Sn);
+                asm volatile("mad.lo.s32 %0, %1, 1, %2;" : "=r"(v[c]) : "r"(Vn), "r"(hg));
+                w[c] = Dn;
+            }
+            if (OP == 19) {   // the traceback cell mix: + 2 ISETP (ALU) + 2 predicated IMAD (FMA)
+                const int In = __viaddmax_s32(v[c], g, w[c]);
+                const int Sn = __dp4a(w[c], hg, v[c]);
+                const int Dn = __viaddmax_s32(w[c], g, In);
+                const int Vn = __vimax3_s32(In, Dn, Sn);
+                asm volatile("{\n\t.reg .pred p1, p2;\n\tsetp.ne.s32 p1, %1, %3;\n\tsetp.ne.and.s32 p2, %2, %3, p1;\n\t"
+                             "@p1 mad.lo.u32 %0, %4, 4, %0;\n\t@p2 mad.lo.u32 %0, %4, 4, %0;\n\t}"
+                             : "+r"(f_acc[c]) : "r"(Sn), "r"(In), "r"(Vn), "r"(one));
+                asm volatile("mad.lo.s32 %0, %1, 1, %2;" : "=r"(v[c]) : "r"(Vn), "r"(hg));
+                w[c] = Dn;
+            }
         }
     }
     const long long t1 = clock64();
     int acc = 0;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) acc ^= v[c] ^ w[c] ^ __float_as_int(f[c]);
+    for (int c = 0; c < CH; ++c) acc ^= v[c] ^ w[c] ^ __float_as_int(f[c]) ^ (int)f_acc[c];
     if (acc == 0x7fffffff) sink[0] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -107,6 +133,11 @@ int main() {
     run<11>("VIADDMNMX imm + IMAD", 2, sms, sink, cyc);
     run<12>("ISETP+SEL", 2, sms, sink, cyc);
     run<13>("2x VIADDMNMX imm (dep pair)", 2, sms, sink, cyc);
+    run<15>("IDP.4A r,r,r", 1, sms, sink, cyc);
+    run<16>("IDP.4A + VIADDMNMX", 2, sms, sink, cyc);
+    run<17>("IDP.4A + IMAD", 2, sms, sink, cyc);
+    run<18>("score-only cell (3 ALU + IDP.4A + IMAD) x5", 5, sms, sink, cyc);
+    run<19>("traceback cell (5 ALU + IDP.4A + 3 IMAD) x9", 9, sms, sink, cyc);
     printf("done %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
