@@ -339,11 +339,13 @@ def score_batch(blob: np.ndarray, off1, len1, off2, len2, scores, is_local: bool
 
 
 def k0_measure() -> dict:
-    """INT32/DPX issue rates measured on this GPU (warp-instructions per clock per SM)."""
+    """INT32/DPX issue rates measured on this GPU, CUDA-event timed (warp-instructions per clock per SM):
+    the ALU pipe (VIADDMNMX, VIMNMX3), the FMA pipe (IMAD, IDP.4A), both together, and the dependency-free instruction
+    mix of one score-only cell (5 instructions) and one traceback cell (9 instructions)."""
     lib = _lib.ensure_init()
-    buf = (C.c_double * 8)()
-    n = lib.gx_k0_measure(buf, 8)
+    buf = (C.c_double * 9)()
+    n = lib.gx_k0_measure(buf, 9)
     if n < 0:
         _lib.check(-n)
-    keys = ["iadd3", "viaddmnmx", "vimnmx3_lop3", "isetp_sel_iadd", "imad", "nw_cells_per_clk_sm", "sm_mhz_attr", "sm_count"]
+    keys = ["viaddmnmx", "vimnmx3", "imad", "idp4a", "alu_fma_pair", "score_cell", "traceback_cell", "sm_ghz", "sm_count"]
     return dict(zip(keys, [float(x) for x in buf]))

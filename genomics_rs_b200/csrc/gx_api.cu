@@ -19,7 +19,7 @@ namespace gx {
 
 static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
 static_assert(sizeof(PairDesc) == 104, "PairDesc layout");
-static_assert(warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
+static_assert(warp_smem_bytes(2) % 16 == 0 && warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
               "per-warp smem must keep 16 B alignment");
 
 // ------------------------------------------------------------------------------------------------
@@ -234,10 +234,11 @@ struct gx_band {
 
 namespace gx {
 
-// (K, R) register tiles the library is built with: K columns x R rows per lane per step (gx_fill.cuh).  R = 1 is the
-// single-row systolic form; R > 1 gives a lone warp instruction-level parallelism across rows and amortises the
-// per-step hand-off over R*K cells.
-#define GX_COMBOS(X) X(4, 1) X(8, 1) X(16, 1) X(4, 4) X(4, 8) X(8, 2) X(8, 4) X(16, 2)
+// (K, R) register tiles the library is built with: K columns x R rows per lane per step (gx_fill.cuh).  R > 1 (several
+// rows per step) is supported by the kernels and was measured on every workload (profiles/r2a_sweep_kr_rowblock.jsonl):
+// the fill is bound by instructions issued per cell, which R does not lower, and the pipeline ramp of a pair grows with R
+// (31 steps of lane skew x R rows per strip), so only R = 1 is instantiated.  Add a pair here and in build.py to try one.
+#define GX_COMBOS(X) X(2, 1) X(4, 1) X(8, 1) X(16, 1)
 
 // the fill kernels are instantiated in gx_fill_inst.cu, one translation unit per (K, R, CHAIN1) so that they build in parallel
 #define GX_DECL(K, R)                                                  \
@@ -593,7 +594,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         // measured on corona shards (tools/timeline_wl.py): 45 pairs K=16 ~ K=8; 23 pairs K=8 ~ K=4 << K=16;
         // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
         pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
-        if (pl->tun.k == 4 || pl->tun.k == 8 || pl->tun.k == 16) pl->K = pl->tun.k;
+        if (pl->tun.k == 2 || pl->tun.k == 4 || pl->tun.k == 8 || pl->tun.k == 16) pl->K = pl->tun.k;
         pl->R = 1;
         if (pl->tun.r > 0 && combo_ok(pl->K, pl->tun.r)) pl->R = pl->tun.r;
         // latency-optimised recurrence (one more ALU op per cell, 1-op row chain) when warps are too few to hide the
@@ -1256,7 +1257,7 @@ int gx_plan_debug_timeline(gx_plan *pl, uint64_t *out, uint64_t cap_words) {
 int gx_debug_tile_order(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs, int K, int bands, uint32_t *out,
                         uint64_t cap_tiles, uint64_t *n_tiles) try {
     if ((!len1 || !len2) && n_pairs) return GX_ERR_ARG;
-    if (!n_tiles || (K != 4 && K != 8 && K != 16)) return GX_ERR_ARG;
+    if (!n_tiles || (K != 2 && K != 4 && K != 8 && K != 16)) return GX_ERR_ARG;
     std::vector<uint32_t> S(n_pairs), P(n_pairs);
     std::vector<uint64_t> sbase(n_pairs, 0);
     uint64_t base = 0, total = 0;

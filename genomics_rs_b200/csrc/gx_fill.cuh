@@ -106,6 +106,29 @@ __device__ __forceinline__ void lds_over_if(int &x, int &y, const uint2 *p, bool
                  : "r"(smem_u32(p)), "r"((uint32_t)pred));
 }
 
+// One profile row (match/mismatch scores of one s1 symbol against this lane's K columns) from shared memory.
+// Layout per symbol: K >= 4: [k/4][lane][k%4] ints -> K/4 conflict-free LDS.128;  K = 2: [lane][2] ints -> one LDS.64.
+template <int K>
+__device__ __forceinline__ void prof_row(const uint8_t *prof_lane /* profile base + lane*min(16, 4K) */, int sym, int *dst) {
+    const uint8_t *row = prof_lane + sym * (K * 128);
+    if constexpr (K >= 4) {
+        const int4 *pp = reinterpret_cast<const int4 *>(row);
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            const int4 v = pp[q * 32];
+            dst[4 * q + 0] = v.x;
+            dst[4 * q + 1] = v.y;
+            dst[4 * q + 2] = v.z;
+            dst[4 * q + 3] = v.w;
+        }
+    } else {
+        static_assert(K == 2, "profile rows exist for K = 2, 4, 8, 16");
+        const int2 v = *reinterpret_cast<const int2 *>(row);
+        dst[0] = v.x;
+        dst[1] = v.y;
+    }
+}
+
 // One batch of BATCH systolic steps of one warp.
 // THRU (last strip of a column band whose width is not a multiple of the strip): padding columns pass (E,I) of
 // the band's last real column through unchanged, so that lane 31 still publishes the band's right boundary.
@@ -174,17 +197,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                     for (int x = 0; x < R * K; ++x) sub[x] = subc[x];
                     // profile rows of the next step (characters fetched one step ago) ...
 #pragma unroll
-                    for (int rr = 0; rr < R; ++rr) {
-                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1a[rr] * (K * 128));
-#pragma unroll
-                        for (int q = 0; q < K / 4; ++q) {
-                            const int4 v = pp[q * 32];
-                            subc[rr * K + 4 * q + 0] = v.x;
-                            subc[rr * K + 4 * q + 1] = v.y;
-                            subc[rr * K + 4 * q + 2] = v.z;
-                            subc[rr * K + 4 * q + 3] = v.w;
-                        }
-                    }
+                    for (int rr = 0; rr < R; ++rr) prof_row<K>(prof_lane, c1a[rr], &subc[rr * K]);
                 } else {
 #pragma unroll
                     for (int rr = 0; rr < R; ++rr) c1[rr] = c1a[rr];
@@ -203,16 +216,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                 for (int rr = 0; rr < R; ++rr) {
                     const int c1 = s1char(r0 + rr);
                     if (PROF) {
-                        // profile layout [sym][k/4][lane][k%4] ints -> K/4 conflict-free LDS.128 per row
-                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
-#pragma unroll
-                        for (int q = 0; q < K / 4; ++q) {
-                            const int4 v = pp[q * 32];
-                            sub[rr * K + 4 * q + 0] = v.x;
-                            sub[rr * K + 4 * q + 1] = v.y;
-                            sub[rr * K + 4 * q + 2] = v.z;
-                            sub[rr * K + 4 * q + 3] = v.w;
-                        }
+                        prof_row<K>(prof_lane, c1, &sub[rr * K]);
                     } else {
 #pragma unroll
                         for (int k = 0; k < K; ++k) sub[rr * K + k] = (c1 == c2[k]) ? ap : bp;
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
     uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);   // 2 x BR entries (double-buffered by batch)
     uint2 *outring = inring + 64;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 64);
-    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints = K*512 bytes
+    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints (K = 2: [4][32][2]) = K*512 bytes
 
     // the s1 staging buffer starts out as valid symbols: unmasked batches prefetch up to 2R bytes past the rows the
     // TMA copy delivered (stale bytes of an earlier tile, or these zeros -- any symbol 0..3 indexes a real profile row)
@@ -412,16 +416,24 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         }
         if (PROF) {
 #pragma unroll
-            for (int sym = 0; sym < 4; ++sym)
+            for (int sym = 0; sym < 4; ++sym) {
+                if constexpr (K >= 4) {
 #pragma unroll
-                for (int q = 0; q < K / 4; ++q) {
-                    int4 v;
-                    v.x = (c2[4 * q + 0] == sym) ? ap : bp;
-                    v.y = (c2[4 * q + 1] == sym) ? ap : bp;
-                    v.z = (c2[4 * q + 2] == sym) ? ap : bp;
-                    v.w = (c2[4 * q + 3] == sym) ? ap : bp;
-                    *reinterpret_cast<int4 *>(prof + sym * (K * 128) + q * 512 + lane * 16) = v;
+                    for (int q = 0; q < K / 4; ++q) {
+                        int4 v;
+                        v.x = (c2[4 * q + 0] == sym) ? ap : bp;
+                        v.y = (c2[4 * q + 1] == sym) ? ap : bp;
+                        v.z = (c2[4 * q + 2] == sym) ? ap : bp;
+                        v.w = (c2[4 * q + 3] == sym) ? ap : bp;
+                        *reinterpret_cast<int4 *>(prof + sym * (K * 128) + q * 512 + lane * 16) = v;
+                    }
+                } else {
+                    int2 v;
+                    v.x = (c2[0] == sym) ? ap : bp;
+                    v.y = (c2[1] == sym) ? ap : bp;
+                    *reinterpret_cast<int2 *>(prof + sym * (K * 128) + lane * 8) = v;
                 }
+            }
         }
 
         // ---- top boundary of the tile: (E,D) of row i0 for this lane's columns
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         }
         phase ^= 1u;
         const uint8_t *s1base = s1buf + delta;
-        const uint8_t *prof_lane = prof + lane * 16;
+        const uint8_t *prof_lane = prof + lane * (K >= 4 ? 16 : 4 * K);
         __syncwarp();   // profile stores visible to the whole warp
         // software-pipelined shared-memory fetches (run_batch, PIPE): profile rows of step 0, characters LOOK-1 steps ahead
         int subc[R * K], c1a[R];
@@ -569,18 +581,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             if (PIPE) {
                 if (PROF) {
 #pragma unroll
-                    for (int rr = 0; rr < R; ++rr) {
-                        const int c1 = s1base[min(max(-lane * R + rr, 0), rows - 1)];
-                        const int4 *pp = reinterpret_cast<const int4 *>(prof_lane + c1 * (K * 128));
-#pragma unroll
-                        for (int q = 0; q < K / 4; ++q) {
-                            const int4 v = pp[q * 32];
-                            subc[rr * K + 4 * q + 0] = v.x;
-                            subc[rr * K + 4 * q + 1] = v.y;
-                            subc[rr * K + 4 * q + 2] = v.z;
-                            subc[rr * K + 4 * q + 3] = v.w;
-                        }
-                    }
+                    for (int rr = 0; rr < R; ++rr) prof_row<K>(prof_lane, s1base[min(max(-lane * R + rr, 0), rows - 1)], &subc[rr * K]);
                 }
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) c1a[rr] = s1base[min(max((LOOK - 1 - lane) * R + rr, 0), rows - 1)];

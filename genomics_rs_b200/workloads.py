@@ -66,33 +66,61 @@ def brca2_pair():
     return s[0][1].encode(), s[1][1].encode()
 
 
-def reads150(first_pair: int, n_pairs: int, length: int = 150, parity_set: bool = False, chunk: int = 1 << 18):
-    """config 4: pair p = (stream 0x5EED0150+2p, stream 0x5EED0150+2p+1), `length` bases each.
-    parity_set: s2 := s1 with each base substituted with probability 1/16 (drawn from the q=1 stream).
-    Returns (blob uint8 [n_pairs*2*length], off1, len1, off2, len2)."""
+def _reads_block(p: np.ndarray, length: int, parity_set: bool):
+    """bases (as ACGT bytes) of the pairs with indices p: ([len(p), length], [len(p), length])"""
+    seeds1 = np.uint64(0x5EED0150) + np.uint64(2) * p.astype(np.uint64)
+    c1 = bases_from_streams(seeds1, length)
+    if parity_set:
+        # the q=1 stream supplies one random byte per base: low nibble == 0 (probability 1/16) substitutes the base
+        nw = (length * 8 + 63) // 64
+        k = np.arange(1, nw + 1, dtype=np.uint64)[None, :]
+        w = splitmix64((seeds1 + np.uint64(1))[:, None], k)
+        by = ((w[:, :, None] >> (np.arange(8, dtype=np.uint64) * np.uint64(8))[None, None, :]) & np.uint64(0xFF)).astype(np.uint8)
+        by = by.reshape(len(p), nw * 8)[:, :length]
+        sub = (by & 0x0F) == 0
+        r = (by >> 4) % 3
+        c2 = np.where(sub, (c1 + 1 + r) % 4, c1).astype(np.uint8)
+    else:
+        c2 = bases_from_streams(seeds1 + np.uint64(1), length)
+    return _LUT[c1], _LUT[c2]
+
+
+def reads150_pairs(indices, length: int = 150, parity_set: bool = False, chunk: int = 1 << 17, threads: int = 0):
+    """config 4: pair p = (stream 0x5EED0150+2p, stream 0x5EED0150+2p+1), `length` bases each, for an arbitrary
+    array of pair indices.  parity_set: s2 := s1 with each base substituted with probability 1/16 (from the q=1 stream).
+    Returns (blob uint8 [n*2*length], off1, len1, off2, len2)."""
+    indices = np.ascontiguousarray(indices, np.uint64)
+    n_pairs = int(indices.size)
     blob = np.empty((n_pairs, 2, length), np.uint8)
-    for s in range(0, n_pairs, chunk):
+
+    def fill(s):
         e = min(n_pairs, s + chunk)
-        p = np.arange(first_pair + s, first_pair + e, dtype=np.uint64)
-        seeds1 = np.uint64(0x5EED0150) + np.uint64(2) * p
-        c1 = bases_from_streams(seeds1, length)
-        if parity_set:
-            # the q=1 stream supplies, per base, 2 random bits pairs: take 6 bits per base from extra words
-            nw = (length * 8 + 63) // 64
-            k = np.arange(1, nw + 1, dtype=np.uint64)[None, :]
-            w = splitmix64((seeds1 + np.uint64(1))[:, None], k)
-            by = ((w[:, :, None] >> (np.arange(8, dtype=np.uint64) * np.uint64(8))[None, None, :]) & np.uint64(0xFF)).astype(np.uint8)
-            by = by.reshape(e - s, nw * 8)[:, :length]
-            sub = (by & 0x0F) == 0                       # probability 1/16
-            r = (by >> 4) % 3
-            c2 = np.where(sub, (c1 + 1 + r) % 4, c1).astype(np.uint8)
-        else:
-            c2 = bases_from_streams(seeds1 + np.uint64(1), length)
-        blob[s:e, 0, :] = _LUT[c1]
-        blob[s:e, 1, :] = _LUT[c2]
+        a, b = _reads_block(indices[s:e], length, parity_set)
+        blob[s:e, 0, :] = a
+        blob[s:e, 1, :] = b
+
+    starts = list(range(0, n_pairs, chunk))
+    threads = threads or min(8, os.cpu_count() or 1)
+    if threads > 1 and len(starts) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:     # numpy releases the GIL inside the big element-wise kernels
+            list(ex.map(fill, starts))
+    else:
+        for s in starts:
+            fill(s)
     base = np.arange(n_pairs, dtype=np.uint64) * np.uint64(2 * length)
     lens = np.full(n_pairs, length, np.uint64)
     return blob.reshape(-1), base, lens, base + np.uint64(length), lens.copy()
+
+
+def reads150(first_pair: int, n_pairs: int, length: int = 150, parity_set: bool = False, chunk: int = 1 << 17):
+    """config 4: the contiguous range of pairs [first_pair, first_pair + n_pairs) (see reads150_pairs)."""
+    return reads150_pairs(np.arange(first_pair, first_pair + n_pairs, dtype=np.uint64), length, parity_set, chunk)
+
+
+# SURVEY 8d, config 4 parity: every score of the parity set's first 100 000 pairs and a strided 1 % of the throughput set
+CONFIG4_PARITY_PAIRS = 100_000
+CONFIG4_STRIDE = 100
 
 
 def long_pair(length: int = 1_000_000):

@@ -323,6 +323,43 @@ def test_read_batch_scores(gx, oracle):
         assert np.array_equal(got, exp)
 
 
+def test_config4_parity_sets(gx, oracle):
+    """BASELINE config 4 as SURVEY 8d specifies its parity: EVERY score of the parity set's first 100 000 pairs
+    (s2 = s1 with 1/16 substitutions) and a strided 1 % of the 10 M-pair throughput set, local SW score only --
+    against the oracle run here and against the frozen fixture (tests/golden/config4_scores.npz), through the streamed
+    host-buffer entry point and through a resident plan; the first pairs also against the FAITHFUL oracle variant."""
+    import os
+    from genomics_rs_b200 import workloads as wl
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "config4_scores.npz"))
+    sets = {"parity": wl.reads150(0, wl.CONFIG4_PARITY_PAIRS, parity_set=True),
+            "strided": wl.reads150_pairs(np.arange(0, 10_000_000, wl.CONFIG4_STRIDE, dtype=np.uint64))}
+    for name, (blob, off1, len1, off2, len2) in sets.items():
+        exp = oracle.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, True, n_threads=8)
+        assert np.array_equal(exp, gold[name].astype(np.int64)), name
+        got = gx.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, True)                 # plan path (< 2^18 pairs)
+        assert np.array_equal(got, exp), name
+        plan = gx.Plan(len1, len2, CONFIG_TOML, True, traceback=False)
+        plan.upload(blob, off1, off2)
+        plan.execute()
+        assert np.array_equal(plan.fetch_scores(), exp), name
+        plan.close()
+        for q in range(0, 300, 7):
+            a = blob[int(off1[q]):int(off1[q]) + 150]
+            b = blob[int(off2[q]):int(off2[q]) + 150]
+            assert oracle.align_faithful(a, b, CONFIG_TOML, True).score == int(got[q]), (name, q)
+    # the streamed path (>= 2^18 pairs): parity set followed by the strided set followed by the parity set again
+    blobs = [sets["parity"], sets["strided"], sets["parity"]]
+    blob = np.concatenate([b[0] for b in blobs])
+    base = np.cumsum([0] + [b[0].size for b in blobs[:-1]]).astype(np.uint64)
+    off1 = np.concatenate([b[1] + o for b, o in zip(blobs, base)])
+    off2 = np.concatenate([b[3] + o for b, o in zip(blobs, base)])
+    len1 = np.concatenate([b[2] for b in blobs])
+    len2 = np.concatenate([b[4] for b in blobs])
+    got = gx.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, True)
+    exp = np.concatenate([gold["parity"], gold["strided"], gold["parity"]]).astype(np.int64)
+    assert got.size >= (1 << 18) and np.array_equal(got, exp)
+
+
 def test_read_stream_scores(gx, oracle):
     """large read sets take the streamed path of gx_score_batch (chunks of 2^20 pairs through two copy/compute lanes):
     more than one chunk, ragged lengths, both modes, offsets that are not multiples of anything"""

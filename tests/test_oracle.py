@@ -104,3 +104,22 @@ def test_corona_golden_sample(oracle, goldens):
     r = oracle.align_linear(s1, s2, CONFIG_TOML, False)
     assert r.score == g["score"] and len(r.ops) == g["n_ops"]
     assert "%016x" % oracle.hash_ops(r.ops, r.start) == g["op_hash"]
+
+
+def test_config4_fixture_is_the_oracle(oracle):
+    """tests/golden/config4_scores.npz (SURVEY 8d config-4 parity sets) is what the oracle computes: a slice of both sets
+    with the batch scorer, a few pairs with the faithful 48-byte-cell variant"""
+    import os
+    import numpy as np
+    from conftest import CONFIG_TOML, GOLDEN
+    from genomics_rs_b200 import workloads as wl
+    gold = np.load(os.path.join(GOLDEN, "config4_scores.npz"))
+    assert gold["parity"].size == wl.CONFIG4_PARITY_PAIRS and gold["strided"].size == 10_000_000 // wl.CONFIG4_STRIDE
+    blob, off1, len1, off2, len2 = wl.reads150(0, 4000, parity_set=True)
+    assert np.array_equal(oracle.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, True, n_threads=4), gold["parity"][:4000])
+    for q in (0, 1, 17, 3999):
+        a, b = blob[int(off1[q]):int(off1[q]) + 150], blob[int(off2[q]):int(off2[q]) + 150]
+        assert oracle.align_faithful(a, b, CONFIG_TOML, True).score == gold["parity"][q]
+    idx = np.arange(0, 10_000_000, wl.CONFIG4_STRIDE, dtype=np.uint64)[-3000:]
+    blob, off1, len1, off2, len2 = wl.reads150_pairs(idx)
+    assert np.array_equal(oracle.score_batch(blob, off1, len1, off2, len2, CONFIG_TOML, True, n_threads=4), gold["strided"][-3000:])

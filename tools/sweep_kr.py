@@ -20,7 +20,7 @@ import genomics_rs_b200 as gx  # noqa: E402
 from genomics_rs_b200 import _lib, workloads as wl  # noqa: E402
 
 SCORES = wl.CONFIG_TOML
-ALL = [(4, 1), (8, 1), (16, 1), (4, 4), (4, 8), (8, 2), (8, 4), (16, 2)]
+ALL = [(2, 1), (4, 1), (8, 1), (16, 1)]
 
 
 def workload(name):
