@@ -100,9 +100,22 @@ def connect_ring(band, group=None) -> None:
     dist.barrier(group=group)   # every inbox is mapped (and initialised) before any kernel may write into it
 
 
-def nw_score_banded(s1, s2, scores, group=None, band_factory=None, steps: int = 1):
+_BAND_CACHE = {}
+
+
+def clear_cache() -> None:
+    """close the bands kept by nw_score_banded(..., cache=True) (collective when they span ranks: call it on every rank)"""
+    for band in _BAND_CACHE.values():
+        band.close()
+    _BAND_CACHE.clear()
+
+
+def nw_score_banded(s1, s2, scores, group=None, band_factory=None, steps: int = 1, cache: bool = False):
     """SPMD: every rank calls this with the same full s1, s2.  Returns (score, band) on every rank; the caller
     owns `band` (band.execute() may be repeated, the same number of times on every rank; band.close()).
+    cache=True keeps the connected band (plan, device buffers, the neighbours' CUDA-IPC mappings) for the next call with
+    the same shape, scores and group -- a stream of equally shaped pairs then pays for creation and the handle exchange
+    once; the returned band belongs to the cache (do not close it; clear_cache() does).
     `band_factory(m, n, world, rank, rank+1, scores)` can be injected (the CPU test uses an oracle-backed band)."""
     import torch
     import torch.distributed as dist
@@ -114,9 +127,15 @@ def nw_score_banded(s1, s2, scores, group=None, band_factory=None, steps: int = 
     if world > 1 and 0 < b.size < world:
         raise ValueError("fewer columns than bands")
     make = band_factory or Band
-    band = make(a.size, b.size, world, rank, rank + 1, scores)
-    if world > 1:
-        connect_ring(band, group)
+    key = (int(a.size), int(b.size), world, rank, tuple(int(x) for x in (scores.as_tuple() if hasattr(scores, "as_tuple") else scores)),
+           id(group), make)
+    band = _BAND_CACHE.get(key) if cache else None
+    if band is None:
+        band = make(a.size, b.size, world, rank, rank + 1, scores)
+        if world > 1:
+            connect_ring(band, group)
+        if cache:
+            _BAND_CACHE[key] = band
     band.upload(a, b)
     for _ in range(steps):
         band.execute()

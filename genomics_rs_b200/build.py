@@ -15,7 +15,7 @@ HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.j
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 # (K, R) register tiles of the fill kernel -- keep in step with GX_COMBOS in csrc/gx_api.cu
-COMBOS = [(2, 1), (4, 1), (8, 1), (16, 1)]
+COMBOS = [(4, 1), (8, 1), (16, 1)]
 # (object name, source, extra flags)
 UNITS = [("gx_api.o", "gx_api.cu", []), ("gx_k0.o", "gx_k0.cu", [])] + [
     (f"gx_fill_k{k}_r{r}_c{c}.o", "gx_fill_inst.cu", [f"-DGX_INST_K={k}", f"-DGX_INST_R={r}", f"-DGX_INST_CHAIN={c}"])

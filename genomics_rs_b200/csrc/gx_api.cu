@@ -7,6 +7,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gxalign.h"
@@ -35,12 +36,14 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<Block> pool;
-    // streamed score batches (gx_score_batch on large read sets): two lanes of copy + kernel
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};
-    cudaEvent_t lane_done[2] = {nullptr, nullptr};
-    int *lane_scores_host[2] = {nullptr, nullptr};   // pinned
-    uint4 *lane_rec_host[2] = {nullptr, nullptr};    // pinned: per-pair records of the chunk in flight
+    // streamed score batches (gx_score_batch on large read sets): NLANES lanes of copy + kernel
+    static constexpr int NLANES = 3;
+    cudaStream_t lane_stream[NLANES] = {nullptr, nullptr, nullptr};
+    cudaEvent_t lane_done[NLANES] = {nullptr, nullptr, nullptr};
+    int *lane_scores_host[NLANES] = {nullptr, nullptr, nullptr};   // pinned
+    uint4 *lane_rec_host[NLANES] = {nullptr, nullptr, nullptr};    // pinned: per-pair records of the chunk in flight
     size_t lane_scores_cap = 0;
+    int host_threads = 1;                             // worker threads for the host passes over a chunk
     uint8_t *ops_stage = nullptr;                     // pinned D2H staging of op lists (grown on demand)
     size_t ops_stage_cap = 0;
     std::string last_error;
@@ -128,7 +131,7 @@ static void pool_free(Ctx *c, void *p) {
 struct Tunables {
     int r = -1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
-        fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0;
+        fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0, test_abort = 0;
 };
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
@@ -150,6 +153,7 @@ static Tunables read_tunables() {
     t.walk_stats = getenv("GX_WALK_STATS") ? 1 : 0;
     t.no_stream = getenv("GX_NO_STREAM") ? 1 : 0;
     t.reads32 = getenv("GX_READS32") ? 1 : 0;
+    t.test_abort = getenv("GX_TEST_ABORT") ? 1 : 0;
     return t;
 }
 
@@ -212,6 +216,7 @@ struct gx_plan {
     bool uploaded = false, executed = false, colbuf_dirty = true;
     float fill_ms = 0, walk_ms = 0;
     int launches = 0;
+    int retries = 0;                   // resident-strips executes that were repeated in ticket mode
     uint64_t h2d_bytes = 0, d2h_bytes = 0, dev_bytes = 0;
     // band plans (gx_band_*): every "pair" is a column band of one wide table
     gx_band *band = nullptr;
@@ -238,7 +243,7 @@ namespace gx {
 // rows per step) is supported by the kernels and was measured on every workload (profiles/r2a_sweep_kr_rowblock.jsonl):
 // the fill is bound by instructions issued per cell, which R does not lower, and the pipeline ramp of a pair grows with R
 // (31 steps of lane skew x R rows per strip), so only R = 1 is instantiated.  Add a pair here and in build.py to try one.
-#define GX_COMBOS(X) X(2, 1) X(4, 1) X(8, 1) X(16, 1)
+#define GX_COMBOS(X) X(4, 1) X(8, 1) X(16, 1)
 
 // the fill kernels are instantiated in gx_fill_inst.cu, one translation unit per (K, R, CHAIN1) so that they build in parallel
 #define GX_DECL(K, R)                                                  \
@@ -297,7 +302,14 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     if (grid_cap > 0 && (uint64_t)grid_cap < cap) cap = grid_cap;
     int grid = (int)std::min<uint64_t>(want, cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, wpc * 32, smem, c->stream>>>(fq);
+    if (pl->resident) {
+        // Resident strips wait for one another, so every CTA of the grid must be on the device at the same time:
+        // a cooperative launch is the only way CUDA guarantees that (the grid fits: checked against the occupancy above).
+        void *kargs[] = {(void *)&fq};
+        CK(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3((unsigned)(wpc * 32)), kargs, smem, c->stream));
+    } else {
+        kern<<<grid, wpc * 32, smem, c->stream>>>(fq);
+    }
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -413,23 +425,34 @@ int gx_init(int device) try {
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < Ctx::NLANES; ++k) {
         CK(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->lane_done[k], cudaEventDisableTiming));
+    }
+    {
+        // host passes of the streamed read path: a few threads per process (one process per GPU shares the host)
+        int ndev = 1;
+        cudaGetDeviceCount(&ndev);
+        const unsigned hw = std::thread::hardware_concurrency();
+        c->host_threads = (int)std::max(1u, std::min(8u, hw / (unsigned)std::max(1, ndev)));
+        if (const char *e = getenv("GX_HOST_THREADS")) c->host_threads = std::max(1, atoi(e));
     }
     g_ctx = c;
     return GX_OK;
 }
 GX_GUARD_END
 
+static void band_cache_drop();   // gx_nw_score_banded keeps its last band object
+
 void gx_shutdown(void) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaStreamSynchronize(g_ctx->stream);
+    band_cache_drop();
     for (auto &b : g_ctx->pool) cudaFree(b.ptr);
     for (auto &e : g_ctx->ev) cudaEventDestroy(e);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < Ctx::NLANES; ++k) {
         if (g_ctx->lane_stream[k]) cudaStreamDestroy(g_ctx->lane_stream[k]);
         if (g_ctx->lane_done[k]) cudaEventDestroy(g_ctx->lane_done[k]);
         if (g_ctx->lane_scores_host[k]) cudaFreeHost(g_ctx->lane_scores_host[k]);
@@ -594,7 +617,7 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         // measured on corona shards (tools/timeline_wl.py): 45 pairs K=16 ~ K=8; 23 pairs K=8 ~ K=4 << K=16;
         // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
         pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
-        if (pl->tun.k == 2 || pl->tun.k == 4 || pl->tun.k == 8 || pl->tun.k == 16) pl->K = pl->tun.k;
+        if (combo_ok(pl->tun.k, 1)) pl->K = pl->tun.k;
         pl->R = 1;
         if (pl->tun.r > 0 && combo_ok(pl->K, pl->tun.r)) pl->R = pl->tun.r;
         // latency-optimised recurrence (one more ALU op per cell, 1-op row chain) when warps are too few to hide the
@@ -726,10 +749,28 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
 
 
 // ------------------------------------------------------------------------------------------------
-// Streamed score batch: large read sets (BASELINE config 4: 10 M x 150 bp) are cut into chunks of pairs that flow
-// through two lanes (stream + device buffers each): while chunk c runs on the SMs, chunk c+1 crosses PCIe and the
-// scores of chunk c-1 come back.  The caller's arrays are used as they are (64-bit offsets and lengths, byte blob):
-// no host-side repack.  Returns GX_ERR_UNSUPPORTED when the batch does not qualify (the caller falls back to a plan).
+// Streamed score batch: large read sets (BASELINE config 4: 10 M x 150 bp) are cut into chunks of 2^18 pairs that flow
+// through NLANES lanes (stream + device buffers each): while chunk c runs on the SMs, chunks c+1, c+2 cross PCIe and the
+// scores of chunk c-1 come back.  The caller's arrays are used as they are (64-bit offsets and lengths, byte blob): the
+// only host work is one validating pass and one pass that packs 16-byte records straight into pinned memory, both
+// split over a few threads.  Returns GX_ERR_UNSUPPORTED when the batch does not qualify (the caller falls back to a plan).
+template <class F>
+static void host_parallel(int threads, uint64_t n, F &&f) {   // f(tid, lo, hi) over [0, n) in `threads` contiguous slices
+    if (threads <= 1 || n < (1u << 15)) {
+        f(0, (uint64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(threads - 1);
+    const uint64_t per = (n + threads - 1) / threads;
+    for (int t = 1; t < threads; ++t) {
+        const uint64_t lo = std::min<uint64_t>(n, per * t), hi = std::min<uint64_t>(n, per * (t + 1));
+        th.emplace_back([&f, t, lo, hi] { f(t, lo, hi); });
+    }
+    f(0, (uint64_t)0, std::min<uint64_t>(n, per));
+    for (auto &t : th) t.join();
+}
+
 static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const uint64_t *off1, const uint64_t *len1,
                                 const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs, gx_scores sc, int is_local,
                                 int64_t *scores, bool force32) {
@@ -740,9 +781,11 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
     int rc = check_scores_impl(sc, READS_MAX_LEN, READS_MAX_LEN, is_local != 0);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
-    const uint64_t CH = 1u << 20;   // pairs per chunk
+    constexpr int NL = Ctx::NLANES;
+    const uint64_t CH = 1u << 18;   // pairs per chunk: ~80 MB of 150 bp reads, ~1.5 ms of PCIe, ~1.5 ms of kernel
+    const int T = std::min(c->host_threads, 16);
     if (c->lane_scores_cap < CH) {
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < NL; ++k) {
             if (c->lane_scores_host[k]) cudaFreeHost(c->lane_scores_host[k]);
             c->lane_scores_host[k] = nullptr;
             if (c->lane_rec_host[k]) cudaFreeHost(c->lane_rec_host[k]);
@@ -763,7 +806,7 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         int *scores = nullptr;
         uint64_t first = 0, count = 0;
         bool busy = false;
-    } lane[2];
+    } lane[NL];
     auto release = [&]() {
         for (auto &L : lane) {
             void *ptrs[] = {L.blob, L.rec, L.scores};
@@ -781,11 +824,15 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         L.busy = false;
         return GX_OK;
     };
-    for (int k = 0; k < 2 && rc == GX_OK; ++k) {
+    for (int k = 0; k < NL && rc == GX_OK; ++k) {
         Lane &L = lane[k];
         rc = pool_alloc(c, CH * sizeof(uint4), (void **)&L.rec);
         if (!rc) rc = pool_alloc(c, CH * 4, (void **)&L.scores);
     }
+    struct Part {
+        uint64_t lo = UINT64_MAX, hi = 0, maxlen = 0, sum = 0, bad = 0;
+    };
+    std::vector<Part> parts((size_t)std::max(T, 1));
     // errors inside the chunk loop leave through `break`: the lanes are drained and their pool blocks released below
 #define CKB(call)                                   \
     {                                               \
@@ -796,21 +843,31 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         }                                           \
     }
     for (uint64_t first = 0, ci = 0; first < n_pairs && rc == GX_OK; first += CH, ++ci) {
-        const int k = (int)(ci & 1);
+        const int k = (int)(ci % NL);
         Lane &L = lane[k];
         const uint64_t count = std::min<uint64_t>(CH, n_pairs - first);
+        const uint64_t *o1 = off1 + first, *o2 = off2 + first, *l1 = len1 + first, *l2 = len2 + first;
         // host pass 1 over the chunk: bounds, longest sequence, byte span of the chunk in the blob (branch-free: vectorises)
-        uint64_t lo = UINT64_MAX, hi = 0, maxlen = 0, sum = 0, badbits = 0;
-        {
-            const uint64_t *o1 = off1 + first, *o2 = off2 + first, *l1 = len1 + first, *l2 = len2 + first;
-            for (uint64_t q = 0; q < count; ++q) {
+        for (auto &p : parts) p = Part();
+        host_parallel(T, count, [&](int tid, uint64_t a, uint64_t b) {
+            Part p;
+            for (uint64_t q = a; q < b; ++q) {
                 const uint64_t a0 = o1[q], a1 = a0 + l1[q], b0 = o2[q], b1 = b0 + l2[q];
-                badbits |= (uint64_t)(a1 > blob_len) | (uint64_t)(b1 > blob_len) | (uint64_t)(a1 < a0) | (uint64_t)(b1 < b0);
-                lo = std::min(lo, std::min(a0, b0));
-                hi = std::max(hi, std::max(a1, b1));
-                maxlen = std::max(maxlen, std::max(l1[q], l2[q]));
-                sum += l1[q] + l2[q];
+                p.bad |= (uint64_t)(a1 > blob_len) | (uint64_t)(b1 > blob_len) | (uint64_t)(a1 < a0) | (uint64_t)(b1 < b0);
+                p.lo = std::min(p.lo, std::min(a0, b0));
+                p.hi = std::max(p.hi, std::max(a1, b1));
+                p.maxlen = std::max(p.maxlen, std::max(l1[q], l2[q]));
+                p.sum += l1[q] + l2[q];
             }
+            parts[(size_t)tid] = p;
+        });
+        uint64_t lo = UINT64_MAX, hi = 0, maxlen = 0, sum = 0, badbits = 0;
+        for (const auto &p : parts) {
+            lo = std::min(lo, p.lo);
+            hi = std::max(hi, p.hi);
+            maxlen = std::max(maxlen, p.maxlen);
+            sum += p.sum;
+            badbits |= p.bad;
         }
         if (badbits) {
             rc = GX_ERR_ARG;
@@ -820,7 +877,7 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
             rc = GX_ERR_UNSUPPORTED;   // long pairs or a scattered blob: not a read stream
             break;
         }
-        rc = drain(k);                 // the chunk that used this lane two rounds ago
+        rc = drain(k);                 // the chunk that used this lane NLANES rounds ago
         if (rc) break;
         const uint64_t span = hi > lo ? hi - lo : 0;
         if (L.blob_cap < span + 64) {
@@ -837,9 +894,10 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         // (lane k's record buffer is free: drain(k) above waited for the chunk that used it)
         {
             uint4 *rec = c->lane_rec_host[k];
-            const uint64_t *o1 = off1 + first, *o2 = off2 + first, *l1 = len1 + first, *l2 = len2 + first;
-            for (uint64_t q = 0; q < count; ++q)
-                rec[q] = make_uint4((uint32_t)(o1[q] - lo), (uint32_t)(o2[q] - lo), (uint32_t)l1[q], (uint32_t)l2[q]);
+            host_parallel(T, count, [&](int, uint64_t a, uint64_t b) {
+                for (uint64_t q = a; q < b; ++q)
+                    rec[q] = make_uint4((uint32_t)(o1[q] - lo), (uint32_t)(o2[q] - lo), (uint32_t)l1[q], (uint32_t)l2[q]);
+            });
         }
         CKB(cudaMemcpyAsync(L.rec, c->lane_rec_host[k], count * sizeof(uint4), cudaMemcpyHostToDevice, st));
         ReadsParams rp;
@@ -867,11 +925,9 @@ static int score_batch_streamed(const uint8_t *blob, uint64_t blob_len, const ui
         L.busy = true;
     }
 #undef CKB
-    if (rc == GX_OK) rc = drain(0);
-    if (rc == GX_OK) rc = drain(1);
+    for (int k = 0; k < NL && rc == GX_OK; ++k) rc = drain(k);
     if (rc != GX_OK) {
-        cudaStreamSynchronize(c->lane_stream[0]);
-        cudaStreamSynchronize(c->lane_stream[1]);
+        for (int k = 0; k < NL; ++k) cudaStreamSynchronize(c->lane_stream[k]);
         cudaGetLastError();
     }
     release();
@@ -973,10 +1029,57 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
 }
 GX_GUARD_END
 
+static int plan_execute_once(gx_plan *pl, bool *aborted);
+
+// Ticket-ordered tile list of a plan (built at creation for ticket plans, on demand when a resident-strips plan falls back)
+static int plan_build_tickets(gx_plan *pl) {
+    Ctx *c = pl->ctx;
+    const size_t np = pl->pairs.size();
+    std::vector<uint32_t> Sv(np), Pv(np);
+    std::vector<uint64_t> sbase(np, 0);
+    uint64_t base = 0;
+    for (size_t q = 0; q < np; ++q) {
+        Sv[q] = pl->pairs[q].S;
+        Pv[q] = pl->pairs[q].P;
+        sbase[q] = base;
+        if (pl->band) base += Sv[q];
+    }
+    std::vector<TileDesc> tiles;
+    tiles.reserve(pl->n_tiles);
+    build_ticket_order(Sv, Pv, sbase, tiles);
+    if (tiles.size() != pl->n_tiles) return GX_ERR_INTERNAL;
+    if (tiles.empty()) return GX_OK;
+    pool_free(c, pl->d_tiles);
+    pl->d_tiles = nullptr;
+    int rc = pool_alloc(c, tiles.size() * sizeof(TileDesc), (void **)&pl->d_tiles);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GX_OK;
+}
+
 int gx_plan_execute(gx_plan *pl) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!pl) return GX_ERR_ARG;
     if (!pl->uploaded) return GX_ERR_ARG;
+    bool aborted = false;
+    int rc = plan_execute_once(pl, &aborted);
+    // A resident-strips fill that gave up waiting (SPIN_LIMIT: the device was shared with something that kept its strips
+    // from running together, or was lost) is repeated ONCE in ticket mode, where a waiting warp only ever waits for
+    // warps that hold earlier tickets.  Band plans that span processes cannot be rewound: they stay failed (poisoned).
+    if (rc == GX_ERR_INTERNAL && aborted && pl->resident && !(pl->band && pl->band->n_bands > pl->band->last - pl->band->first)) {
+        pl->resident = false;
+        pl->retries++;
+        int rb = plan_build_tickets(pl);
+        if (rb) return rb;
+        pl->colbuf_dirty = true;     // the aborted execute left the LL parity words in an unknown state
+        rc = plan_execute_once(pl, &aborted);
+    }
+    return rc;
+}
+GX_GUARD_END
+
+static int plan_execute_once(gx_plan *pl, bool *aborted) {
     Ctx *c = pl->ctx;
     CK(cudaSetDevice(c->device));
     pl->launches = 0;
@@ -1143,9 +1246,11 @@ int gx_plan_execute(gx_plan *pl) try {
     }
     if (fp.stats) CK(cudaMemcpyAsync(pl->h_stats, pl->d_stats, 64, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (pl->tun.test_abort && pl->resident && pl->retries == 0) abort_word = 1;   // test hook: exercise the ticket-mode retry
     if (abort_word || abort_word2) {
         g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";
         if (bd && bd->n_bands > bd->last - bd->first) bd->poisoned = true;
+        *aborted = true;
         return GX_ERR_INTERNAL;
     }
     if (bd) bd->epoch++;
@@ -1157,7 +1262,6 @@ int gx_plan_execute(gx_plan *pl) try {
     pl->executed = true;
     return GX_OK;
 }
-GX_GUARD_END
 
 int gx_plan_fetch(gx_plan *pl, gx_result *out, uint8_t *ops_blob, const uint64_t *ops_off) try {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -1300,6 +1404,8 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 9: return (double)pl->kind;
         case 15: return (double)pl->K;
         case 19: return (double)pl->R;
+        case 20: return (double)pl->retries;
+        case 21: return pl->resident ? 1.0 : 0.0;
         case 17: return pl->chain1 ? 1.0 : 0.0;
         case 18: return pl->lcs_ms;
         case 10: case 11: case 12: case 13: case 14: return (double)pl->h_stats[what - 10];
@@ -1528,16 +1634,33 @@ void gx_band_destroy(gx_band *b) {
     band_free(b);
 }
 
+// The band object of the last gx_nw_score_banded call is kept (geometry, tile lists, device buffers): a caller that
+// scores a stream of equally shaped pairs pays for plan creation once.  Released by gx_shutdown or by a call with
+// another shape; its device memory comes from the context's caching pool either way.
+static gx_band *g_band_cache = nullptr;
+static void band_cache_drop() {
+    if (g_band_cache) band_free(g_band_cache);
+    g_band_cache = nullptr;
+}
+
 int gx_nw_score_banded(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n, gx_scores sc, int n_bands, int64_t *score) try {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!score || (!s1 && m) || (!s2 && n)) return GX_ERR_ARG;
-    gx_band *b = nullptr;
-    int rc = gx_band_create(m, n, n_bands, 0, n_bands, sc, &b);
-    if (rc) return rc;
+    gx_band *b = g_band_cache;
+    const bool hit = b && b->m == m && b->n_total == n && b->n_bands == n_bands && b->first == 0 && b->last == n_bands &&
+                     memcmp(&b->sc, &sc, sizeof sc) == 0 && !b->poisoned;
+    if (!hit) {
+        band_cache_drop();
+        b = nullptr;
+        int rc = gx_band_create(m, n, n_bands, 0, n_bands, sc, &b);
+        if (rc) return rc;
+        g_band_cache = b;
+    }
     int valid = 0;
-    rc = gx_band_upload(b, s1, s2);
+    int rc = gx_band_upload(b, s1, s2);
     if (!rc) rc = gx_band_execute(b);
     if (!rc) rc = gx_band_score(b, score, &valid);
-    gx_band_destroy(b);
+    if (rc) band_cache_drop();
     return rc;
 }
 GX_GUARD_END

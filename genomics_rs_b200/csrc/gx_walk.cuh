@@ -292,8 +292,11 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 j = j_none ? 0u : j - run * dj;
                 if (i == 0 && j == 0) break;
                 // lane `run` looked at exactly (i, j) unless the run used all 32 lanes, the move was clamped, or that
-                // cell was outside the window (7): then look it up (and reload the window at the top of the loop)
-                c0 = (run < 32u && !i_none && !j_none && c_next != 7u) ? c_next : cell_code(i, j);
+                // cell was outside the window (7): then look it up (and reload the window at the top of the loop).
+                // A warp-uniform branch: one lone warp runs the walk, so instructions issued are what an iteration
+                // costs, and the second lookup is a fifth of them.
+                if (run < 32u && !i_none && !j_none && c_next != 7u) c0 = c_next;
+                else c0 = cell_code(i, j);
             }
             res.end_i = end_i;
             res.end_j = end_j;

@@ -14,7 +14,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 CONFIG_TOML = (1, -2, -1, -5)   # reference config.toml
 TEST_CONFIG = (1, -2, -2, -5)   # reference tests/test_alignment.rs:4-11
 # (K, R) register tiles the fill kernel is built with (GX_COMBOS in csrc/gx_api.cu): K columns x R rows per lane per step
-KR_COMBOS = [(2, 1), (4, 1), (8, 1), (16, 1)]
+KR_COMBOS = [(4, 1), (8, 1), (16, 1)]
 
 
 def force_kr(monkeypatch, k, r):

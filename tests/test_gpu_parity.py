@@ -198,6 +198,28 @@ def test_plan_reexecute_is_idempotent(gx, oracle):
     plan.close()
 
 
+def test_resident_abort_falls_back_to_tickets(gx, oracle, monkeypatch):
+    """a resident-strips execute that gives up waiting (SPIN_LIMIT) is repeated once in ticket mode: same results,
+    the plan stays usable (GX_TEST_ABORT fakes the abort word of the first execute)"""
+    rng = np.random.default_rng(3)
+    pairs = [random_pair(rng, 5000, 3000), random_pair(rng, 900, 2500)]
+    blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+    monkeypatch.setenv("GX_TEST_ABORT", "1")
+    plan = gx.Plan(len1, len2, CONFIG_TOML, False, traceback=True)
+    monkeypatch.delenv("GX_TEST_ABORT")
+    plan.upload(blob, off1, off2)
+    assert plan.stat(21) == 1.0                       # few strips: resident mode (cooperative launch)
+    for it in range(3):
+        plan.execute()
+        assert plan.stat(20) == 1.0 and plan.stat(21) == 0.0   # retried once, ticket mode from then on
+        res, ops, ops_off = plan.fetch()
+        for q, (a, b) in enumerate(pairs):
+            o = oracle.align_linear(a, b, CONFIG_TOML, False)
+            assert res["score"][q] == o.score
+            assert np.array_equal(ops[int(ops_off[q]):int(ops_off[q]) + int(res["n_ops"][q])], o.ops)
+    plan.close()
+
+
 def test_corona_all_vs_all(gx, oracle, goldens):
     """BASELINE config 3: 45 pairs of ~30 kb genomes, global, score + traceback, one batch."""
     order = goldens["corona_order"]

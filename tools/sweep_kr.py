@@ -20,7 +20,7 @@ import genomics_rs_b200 as gx  # noqa: E402
 from genomics_rs_b200 import _lib, workloads as wl  # noqa: E402
 
 SCORES = wl.CONFIG_TOML
-ALL = [(2, 1), (4, 1), (8, 1), (16, 1)]
+ALL = [(4, 1), (8, 1), (16, 1)]
 
 
 def workload(name):
