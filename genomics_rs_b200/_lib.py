@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgxalign.so")
+LIB_PATH = os.environ.get("GX_LIB_PATH") or os.path.join(_HERE, "libgxalign.so")   # GX_LIB_PATH: A/B builds of the library
 
 GX_OK = 0
 GX_FLAG_TRACEBACK = 1

@@ -9,11 +9,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-OUT = os.path.join(HERE, "libgxalign.so")
+# A/B builds: GX_BUILD_TAG=b16 GX_BUILD_DEFS="-DGX_BMIN=16" python -m genomics_rs_b200.build  ->  libgxalign_b16.so
+TAG = os.environ.get("GX_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + TAG if TAG else ""))
+OUT = os.path.join(HERE, "libgxalign" + ("_" + TAG if TAG else "") + ".so")
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "gxalign.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CFLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+CFLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"] + os.environ.get("GX_BUILD_DEFS", "").split()
 # (K, R) register tiles of the fill kernel -- keep in step with GX_COMBOS in csrc/gx_api.cu
 COMBOS = [(4, 1), (8, 1), (16, 1)]
 # (object name, source, extra flags)

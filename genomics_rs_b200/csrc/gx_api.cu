@@ -129,7 +129,7 @@ static void pool_free(Ctx *c, void *p) {
 // Debug / experiment switches.  The environment is read ONCE per plan (gx_plan_create) or per streamed
 // batch call, never on the execute path; -1 = not set.
 struct Tunables {
-    int r = -1;
+    int r = -1, batch = -1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
         fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0, test_abort = 0;
 };
@@ -141,6 +141,7 @@ static Tunables read_tunables() {
     Tunables t;
     t.k = env_int("GX_K", -1);
     t.r = env_int("GX_R", -1);
+    t.batch = env_int("GX_BATCH", -1);
     t.chain1 = env_int("GX_CHAIN1", -1);
     t.tickets = getenv("GX_TICKETS") ? 1 : -1;
     t.resident = env_int("GX_RESIDENT", -1);
@@ -171,6 +172,7 @@ struct gx_plan {
     gx::Tunables tun;                  // debug switches as they were when the plan was created
     int is_local = 0, flags = 0;
     int K = 8, R = 1;                  // register tile of the fill: K columns x R rows per lane per step
+    uint32_t cpb = 1;                  // code chunks per hand-off batch (batch = cpb * 64/(R*K) steps)
     bool chain1 = false;               // latency-optimised recurrence (gx_fill.cuh, CHAIN1)
     int track = 0;
     bool traceback = false;
@@ -331,7 +333,8 @@ static int launch_walk(gx_plan *pl, const WalkParams &wp) {
     }
     const uint32_t smem = wp.traceback ? smem_max : 0u;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    kern<<<(unsigned)pl->n_pairs, 32, smem, pl->ctx->stream>>>(wp);
+    // one CTA per pair: path warp + emit warp with traceback, a single warp (start cell and score only) without
+    kern<<<(unsigned)pl->n_pairs, wp.traceback ? 64 : 32, smem, pl->ctx->stream>>>(wp);
     CK(cudaGetLastError());
     return GX_OK;
 }
@@ -616,7 +619,10 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
             }
         // measured on corona shards (tools/timeline_wl.py): 45 pairs K=16 ~ K=8; 23 pairs K=8 ~ K=4 << K=16;
         // 11 pairs K=4 6.1 ms vs K=8 8.5 ms; 6 pairs K=4 5.5 vs K=8 7.0 -- shorter strips win until the warp slots are full
-        pl->K = (strips16 * 10 >= resident * 9) ? 16 : ((strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4);
+        // round 2 (32-step batches in ticket mode, profiles/r2e_sweep_batch_b32.jsonl): K=8 beats K=16 wherever both fill the
+        // warp slots (45 pairs 16.7 vs 17.3 ms, 1 Mbp x 1 Mbp 282 vs 340 ms), so K=16 is no longer picked by itself
+        (void)strips16;
+        pl->K = (strips8 * 10 >= resident * 12 || max_len < 2048) ? 8 : 4;
         if (combo_ok(pl->tun.k, 1)) pl->K = pl->tun.k;
         pl->R = 1;
         if (pl->tun.r > 0 && combo_ok(pl->K, pl->tun.r)) pl->R = pl->tun.r;
@@ -632,7 +638,27 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         if (pl->tun.chain1 >= 0) pl->chain1 = pl->tun.chain1 != 0;
     }
     const int K = pl->K, R = pl->R, W = 32 * K;
-    const uint32_t SPC = 64u / (uint32_t)(R * K), BATCH = (uint32_t)geo_batch(K, R), CPB = BATCH / SPC;
+    // resident-strips mode: every strip of the plan fits a warp slot of its own (single-warp CTAs, 16 per SM: the
+    // launch bounds cap the registers at 128 and 16 x (per-warp shared memory + 1 KB) fits the SM for every K)
+    {
+        const uint64_t ns = pl->n_strips;
+        // measured: 41 % of the warp slots (980 strips) 96 -> 76 ms, 60 % (6 corona pairs) 5.5 -> 4.6 ms, 83 % (1954 strips)
+        // 352 -> 357 ms: with most slots busy the ticket order's interleaving of panels does as well, so stop at 70 %
+        pl->resident = ns > 0 && ns * 10 <= (uint64_t)c->sm_count * warps_per_sm(K) * 7 && pl->tun.tickets < 0;
+        if (pl->tun.resident >= 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = pl->tun.resident != 0;
+    }
+    // hand-off batch length (gx_fill.cuh, Geo): 32 steps when the plan keeps every warp slot busy (ticket mode: the per-batch
+    // glue is what is left to amortise), short batches when the pipeline ramp of a pair -- strips x (31 + batch) steps --
+    // is where the time goes (resident strips).  profiles/r2e_sweep_batch_*.jsonl.
+    const uint32_t SPC = 64u / (uint32_t)(R * K), CPB_MAX = std::max(1u, 32u / (SPC * (uint32_t)R));
+    {
+        uint32_t steps = pl->resident ? (K >= 16 ? 16u : 8u) : 32u;
+        if (pl->tun.batch > 0) steps = (uint32_t)pl->tun.batch;
+        uint32_t cpb = std::max(1u, steps / SPC);
+        while (cpb & (cpb - 1)) cpb &= cpb - 1;          // power of two
+        pl->cpb = std::min(cpb, CPB_MAX);
+    }
+    const uint32_t CPB = pl->cpb, BATCH = CPB * SPC;
     pl->pairs.resize(n_pairs);
     std::vector<TileDesc> tiles;
     std::vector<uint64_t> sbase(n_pairs, 0);
@@ -676,16 +702,6 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     if (n_tiles_total >= (1ull << 32) - 65536) {
         delete pl;
         return GX_ERR_RANGE;
-    }
-    // resident-strips mode: every strip of the plan fits a warp slot of its own (single-warp CTAs, 16 per SM: the
-    // launch bounds cap the registers at 128 and 16 x (per-warp shared memory + 1 KB) fits the SM for every K)
-    {
-        uint64_t ns = 0;
-        for (uint64_t q = 0; q < n_pairs; ++q) ns += pl->pairs[q].S;
-        // measured: 41 % of the warp slots (980 strips) 96 -> 76 ms, 60 % (6 corona pairs) 5.5 -> 4.6 ms, 83 % (1954 strips)
-        // 352 -> 357 ms: with most slots busy the ticket order's interleaving of panels does as well, so stop at 70 %
-        pl->resident = ns > 0 && ns * 10 <= (uint64_t)c->sm_count * warps_per_sm(K) * 7 && pl->tun.tickets < 0;
-        if (pl->tun.resident >= 0 && ns <= (uint64_t)c->sm_count * warps_per_sm(K)) pl->resident = pl->tun.resident != 0;
     }
     if (!pl->resident) {
         std::vector<uint32_t> Sv(n_pairs), Pv(n_pairs);
@@ -1165,6 +1181,7 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
     fp.n_tiles = (uint32_t)pl->n_tiles;
     fp.pmax = 0;   // launch_fill switches to the [strip][panel] list when every strip gets a warp
     fp.parity = pl->parity;
+    fp.cpb = pl->cpb;
     fp.epoch = bd ? bd->epoch + 1 : 0;
     fp.ticket = pl->d_ctrl;
     fp.progress = pl->d_ctrl + 16;
@@ -1405,6 +1422,7 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 15: return (double)pl->K;
         case 19: return (double)pl->R;
         case 20: return (double)pl->retries;
+        case 22: return (double)(pl->cpb * (64u / (uint32_t)(pl->R * pl->K)));   // steps per hand-off batch
         case 21: return pl->resident ? 1.0 : 0.0;
         case 17: return pl->chain1 ? 1.0 : 0.0;
         case 18: return pl->lcs_ms;

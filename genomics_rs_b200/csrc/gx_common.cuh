@@ -71,6 +71,7 @@ struct FillParams {
     uint32_t n_tiles;
     uint32_t pmax;                   // resident-strips mode: tiles are laid out [strip][panel] with pmax entries per strip; else 0
     uint32_t parity;                 // LL parity bit of this execute (SURVEY "boundary hand-off")
+    uint32_t cpb;                    // code chunks per hand-off batch (batch = cpb * SPC steps <= 32 rows)
     uint32_t epoch;                  // 1-based execute number of a band plan (see PairDesc::ack), else 0
     uint32_t *ticket;
     uint32_t *progress;

@@ -75,22 +75,23 @@ __device__ __forceinline__ void code_acc(uint32_t &cw, int S, int I, int V, uint
 // step (an R x K register tile); the 32 lanes of a warp run a systolic skew in units of row blocks: at step t lane l
 // updates row block t-l.  Steps are unrolled one 16-byte code chunk at a time (SPC steps = 64 cells per lane) and
 // the boundary hand-off between strips works in batches of BATCH steps = BATCH*R rows (<= 32: one row per lane).
+// A lane owns K consecutive columns and works on R consecutive rows per step (an R x K register tile); steps are unrolled
+// one 16-byte code chunk at a time (SPC steps = 64 cells per lane).  The boundary hand-off between strips works in batches
+// of `cpb` chunks = cpb*SPC steps, a RUN-TIME parameter of the plan (FillParams::cpb, 1..32/(SPC*R)): the per-batch glue
+// (publish the right boundary, settle the left one, two warp syncs) costs ~170 instructions, which 8 steps of K = 8 columns
+// cannot amortise (2.7 instructions per cell), while a strip trails its left neighbour by 31 + batch steps -- long batches
+// for plans that keep every warp slot busy, short ones where the pipeline ramp of a pair is what the time goes into
+// (profiles/r2e_sweep_batch_*.jsonl: 1 Mbp x 1 Mbp 322 -> 282 ms, 45 coronavirus pairs 17.9 -> 16.7 ms at 32 steps; one
+// BRCA2 pair 1.0 -> 1.4 ms).  At most 32 rows per batch: one boundary row per lane.
 template <int K, int R>
 struct Geo {
     static_assert(R * K <= 64 && (R & (R - 1)) == 0 && (K & (K - 1)) == 0, "R x K cells must fit one 16-byte code chunk");
     static constexpr int W = 32 * K;                       // columns per strip
     static constexpr int SPC = 64 / (R * K);               // steps per 16-byte code chunk
-    static constexpr int BMIN = (32 / R < 8) ? 32 / R : 8;
-    static constexpr int BATCH = (SPC > BMIN) ? SPC : BMIN;   // steps per batch (boundary hand-off granularity)
-    static constexpr int CPB = BATCH / SPC;                // code chunks per batch
-    static constexpr int BR = BATCH * R;                   // rows per batch
+    static constexpr int CPB_MAX = 32 / (SPC * R) > 0 ? 32 / (SPC * R) : 1;   // chunks per batch: at most 32 rows per batch
     static constexpr int KB = Log2<K>::value;
-    static_assert(BR <= 32, "one boundary row per lane");
+    static_assert(SPC * R <= 32, "one chunk must not exceed 32 rows");
 };
-__host__ __device__ constexpr int geo_batch(int K, int R) {
-    const int spc = 64 / (R * K), bmin = (32 / R < 8) ? 32 / R : 8;
-    return spc > bmin ? spc : bmin;
-}
 // batches of one tile: row blocks (rows rounded up to R) + 31 steps of skew, in batches of `batch` steps
 __host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_t R, uint32_t batch) {
     return ((rows + R - 1) / R + 31 + batch - 1) / batch;
@@ -157,7 +158,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                                           const uint2 *inr /* left-boundary (E,I) of this batch's rows */, uint2 *outring, uint4 *code_dst,
                                           const int t0, const int rows, const int lane, const int kvalid,
                                           int (&subc)[R * K] /* PIPE+PROF: profile rows of the step about to run */,
-                                          int (&c1a)[R] /* PIPE: s1 characters LOOK-1 steps ahead */) {
+                                          int (&c1a)[R] /* PIPE: s1 characters LOOK-1 steps ahead */, const int cpb /* chunks in this batch */) {
     using G = Geo<K, R>;
     constexpr int KB = G::KB;
     constexpr bool PIPE = (R * K <= 16) && (K < 16);
@@ -170,7 +171,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
         return (int)s1base[r];
     };
 #pragma unroll 1
-    for (int ch = 0; ch < G::CPB; ++ch) {
+    for (int ch = 0; ch < cpb; ++ch) {
         uint32_t cw[4] = {0u, 0u, 0u, 0u};
         static_for<G::SPC>([&](auto uc) {
             constexpr int uu = decltype(uc)::value;
@@ -329,8 +330,9 @@ template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN
 __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(const FillParams P) {
     using G = Geo<K, R>;
     constexpr int W = G::W;
-    constexpr int B = G::BATCH;     // steps per batch
-    constexpr int BR = G::BR;       // rows per batch
+    const int cpb = (int)P.cpb;          // code chunks per hand-off batch (run-time: see Geo)
+    const int B = cpb * G::SPC;          // steps per batch
+    const int BR = B * R;                // rows per batch (<= 32)
     constexpr int KB = G::KB;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -671,17 +673,17 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
             for (; bt < m_end && !dead; ++bt) {
                 uint2 *outr = outring + (bt & 1u) * BR;
-                uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                 if constexpr (!LOCAL && !CODES && TRACK == 0) {
                     if (thru)
                         run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                            one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                           (int)(B * bt), rows, lane, kvalid, subc, c1a);
+                                                                                           (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
                 }
                 if (!thru)
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                         one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                        (int)(B * bt), rows, lane, kvalid, subc, c1a);
+                                                                                        (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
@@ -691,19 +693,19 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             if ((TRACK != 0) && has_pad && P.pad_keys != 0u) {
                 for (; bt < nb_body && !dead; ++bt) {
                     uint2 *outr = outring + (bt & 1u) * BR;
-                    uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                    uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                 (int)(B * bt), rows, lane, kvalid, subc, c1a);
+                                                                                 (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
                     if (!post(bt, outr)) dead = true;
                 }
             } else {
                 for (; bt < nb_body && !dead; ++bt) {
                     uint2 *outr = outring + (bt & 1u) * BR;
-                    uint4 *cdst = CODES ? code_base + (size_t)bt * G::CPB * 32 : nullptr;
+                    uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                   one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                  (int)(B * bt), rows, lane, kvalid, subc, c1a);
+                                                                                  (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
                     if (!post(bt, outr)) dead = true;
                 }
             }

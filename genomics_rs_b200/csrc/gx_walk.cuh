@@ -19,19 +19,44 @@
 
 namespace gx {
 
-// dynamic shared memory of one walk warp: two window buffers (codes + label characters).
+// dynamic shared memory of one walk CTA: a 1 KB control block (descriptor ring between the two warps, head / tail words,
+// debug counters) and two code-window buffers.
 // A window is 256 rows of one strip = 256/R (+1) row blocks + 31 steps of lane skew, 64/(R*K) steps per code chunk.
 __host__ __device__ constexpr uint32_t walk_chunks(int K, int R) { return (uint32_t)((256 / R + 1 + 31 + 64 / (R * K) - 1) / (64 / (R * K)) + 1); }
-__host__ __device__ constexpr uint32_t walk_buf_bytes(int K, int R) {
-    return (uint32_t)(walk_chunks(K, R) * 32 * 16 + (256 + 32) + (32 * K + 32) + 15) & ~15u;
-}
-__host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R) { return 2 * walk_buf_bytes(K, R); }
+__host__ __device__ constexpr uint32_t walk_buf_bytes(int K, int R) { return walk_chunks(K, R) * 32 * 16; }
+constexpr uint32_t WALK_CTRL_BYTES = 1024;
+constexpr uint32_t WALK_RING = 32;          // run descriptors in flight between the path warp and the emit warp
+__host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R) { return WALK_CTRL_BYTES + 2 * walk_buf_bytes(K, R); }
 
+__device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_volatile_uint4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// One CTA of TWO warps per pair (one warp when no traceback is wanted).  The walk is m+n dependent steps, so what it costs
+// is the instructions ONE warp has to issue per step of the dependent chain (a lone warp issues ~0.4 instructions per
+// clock).  The chain is therefore kept to the path finding alone:
+//   path warp (warp 0)  follows the stored direction codes: code windows in shared memory (cp.async, double-buffered,
+//                       next window prefetched), run following (lane x inspects the cell x moves ahead, a ballot gives
+//                       the run length), and pushes one descriptor (i, j, direction, run length) per run into a ring;
+//   emit warp (warp 1)  pops descriptors and does everything that is not on the chain: the off-by-one match labels
+//                       is_match(i, j) (characters straight from global memory / L1), open/extend labels, the four
+//                       counters, the coalesced op stores, the end cell.
 template <int K, int R>
-__global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
     const uint32_t q = blockIdx.x;
     if (q >= P.n_pairs) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
     const PairDesc *pd = P.pairs + q;
     const uint32_t m = pd->m, n = pd->n;
     const uint8_t *s1 = P.blob + pd->s1_off;
@@ -101,29 +126,48 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
     res.lcs_at_first_max = 0;
     res.fill_ms = res.walk_ms = 0.0;
 
-    if (P.traceback) {
-        using G = Geo<K, R>;
-        constexpr int SPC = G::SPC;
-        constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
-        constexpr int NCH = (int)walk_chunks(K, R);           // code chunks per fill-lane in a window
-        // Two window buffers in dynamic shared memory: the walk reads buffer `cb`; the other one receives the window the
-        // walk will probably need next (prefetched with cp.async while the walk runs).  Per buffer: code chunks
-        // [chunk][fill-lane] + the label characters of the window: is_match(i,j) reads s1[i] and s2[j] (0-based: the
-        // characters AFTER the cell's own, algo.rs:354), i.e. s1[i0w+1 ..] for the rows and s2[j0w+1 ..] for the columns.
-        extern __shared__ __align__(16) uint8_t walk_smem[];
+    if (!P.traceback) {
+        if (threadIdx.x == 0) P.results[q] = res;
+        return;
+    }
+    using G = Geo<K, R>;
+    constexpr int SPC = G::SPC;
+    constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
+    constexpr int NCH = (int)walk_chunks(K, R);           // code chunks per fill-lane in a window
+    extern __shared__ __align__(16) uint8_t walk_smem[];
+    uint4 *ring = reinterpret_cast<uint4 *>(walk_smem);                                   // WALK_RING descriptors {i, j, code | run << 8, -}
+    uint32_t *head = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16);             // descriptors pushed (path warp)
+    uint32_t *tail = head + 1;                                                             // descriptors consumed (emit warp)
+    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(walk_smem + WALK_RING * 16 + 16);
+    uint8_t *bufs = walk_smem + WALK_CTRL_BYTES;
+    if (threadIdx.x == 0) {
+        sts_volatile_u32(head, 0u);
+        sts_volatile_u32(tail, 0u);
+    }
+    __syncthreads();
+
+    if (wid == 0) {
+        // ================================================================ path warp
+        // Two window buffers: the walk reads buffer `cb`; the other one receives the window the walk will probably need
+        // next (prefetched with cp.async while the walk runs).  Per buffer: code chunks [chunk][fill-lane].
         constexpr uint32_t BUF_BYTES = walk_buf_bytes(K, R);
         uint32_t cb = 0;
-        const uint4 *win = reinterpret_cast<const uint4 *>(walk_smem);
-        const uint8_t *s1w = walk_smem + NCH * 32 * 16;
-        const uint8_t *s2w = s1w + (WR + 32);
-        uint32_t s1w0 = 0, s2w0 = 0;                          // sequence index of s1w[0] / s2w[0]
+        const uint4 *win = reinterpret_cast<const uint4 *>(bufs);
         // prefetched window (in buffer cb ^ 1): tile (np, ns), local rows [nr0, nr1]; np = 0xffffffff: none
         uint32_t np = 0xffffffffu, ns = 0, nr0 = 0, nr1 = 0;
-        uint8_t *ops = P.ops + pd->ops_off;
-        uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
-        uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
         // current window: tile (wp, ws), local rows [wr0, wr1], first chunk wc0
         uint32_t wp = 0xffffffffu, ws = 0, wr0 = 0, wr1 = 0, wc0 = 0;
+        uint32_t pushed = 0;
+        auto push = [&](uint32_t pi, uint32_t pj, uint32_t meta) __attribute__((always_inline)) {
+            if (lane == 0) {
+                while (pushed - lds_volatile_u32(tail) >= WALK_RING) {
+                }
+                ring[pushed % WALK_RING] = make_uint4(pi, pj, meta, 0u);
+                __threadfence_block();                       // descriptor before the head word
+                sts_volatile_u32(head, pushed + 1u);
+            }
+            pushed++;
+        };
 
         // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (a run must end before it)
         // Straight-line (no branches): the lookup is on the loop-carried chain of the walk.
@@ -146,14 +190,8 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
         unsigned long long dbg_iters = 0, dbg_reloads = 0;
         long long dbg_reload_cyc = 0;
         const long long dbg_t0 = clock64();
-        if (i == 0 && j == 0) {
-            // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
-            if (lane == 0) ops[0] = 0;
-            nops = 1;
-            n_match = 1;
-        } else {
+        if (!(i == 0 && j == 0)) {
             uint32_t c0 = cell_code(i, j);
-            uint32_t end_i = i, end_j = j;
             for (;;) {
                 dbg_iters++;
                 if (c0 == 7u) {
@@ -168,7 +206,7 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                         const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
                                                                              (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
                                             (size_t)c0w * 32 + lane;
-                        uint32_t dst = smem_u32(walk_smem + b * BUF_BYTES) + (uint32_t)lane * 16u;
+                        uint32_t dst = smem_u32(bufs + b * BUF_BYTES) + (uint32_t)lane * 16u;
                         for (uint32_t q2 = 0; q2 < nch; ++q2) {
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)q2 * 32) : "memory");
                             dst += 32 * 16;
@@ -195,32 +233,7 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                     }
                     np = 0xffffffffu;
                     wc0 = (wr0 / R) / SPC;
-                    uint8_t *base = walk_smem + cb * BUF_BYTES;
-                    win = reinterpret_cast<const uint4 *>(base);
-                    uint8_t *s1wm = base + NCH * 32 * 16, *s2wm = s1wm + (WR + 32);
-                    s1w = s1wm;
-                    s2w = s2wm;
-                    // label characters: rows wr0..wr1 of panel wp -> s1 indices (i-1)+1, columns of strip ws -> s2 indices (j-1)+1
-                    s1w0 = (wp << PANEL_H_LOG2) + wr0 + 1u;
-                    s2w0 = ws * G::W + 1u;
-                    // (all loads first, then the stores: one memory latency for the whole window, not one per byte)
-                    {
-                        uint8_t a1[WR / 32], a2[K];
-#pragma unroll
-                        for (int q2 = 0; q2 < WR / 32; ++q2) {
-                            const uint32_t k = (uint32_t)lane + 32u * q2;
-                            a1[q2] = (k <= wr1 - wr0 && s1w0 + k < m) ? __ldg(s1 + s1w0 + k) : (uint8_t)0;
-                        }
-#pragma unroll
-                        for (int q2 = 0; q2 < K; ++q2) {
-                            const uint32_t k = (uint32_t)lane + 32u * q2;
-                            a2[q2] = (s2w0 + k < n) ? __ldg(s2 + s2w0 + k) : (uint8_t)0;
-                        }
-#pragma unroll
-                        for (int q2 = 0; q2 < WR / 32; ++q2) s1wm[lane + 32 * q2] = a1[q2];
-#pragma unroll
-                        for (int q2 = 0; q2 < K; ++q2) s2wm[lane + 32 * q2] = a2[q2];
-                    }
+                    win = reinterpret_cast<const uint4 *>(bufs + cb * BUF_BYTES);
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
                     c0 = cell_code(i, j);
@@ -254,7 +267,6 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
                 // every lane looks x steps ahead in the direction of c0; the run ends at the first different code
                 const uint32_t x = (uint32_t)lane;
-                const bool diag = (c0 == 0u);
                 const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
                 const bool reach = (x * di <= i) & (x * dj <= j);
                 const uint32_t ci = i - (reach ? x * di : 0u), cj = j - (reach ? x * dj : 0u);
@@ -264,28 +276,8 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
                 // the cell the walk reaches next is the one lane `run` just looked at: its code starts the next iteration
                 const uint32_t c_next = __shfl_sync(0xffffffffu, cx, (int)(run & 31u));
-                const bool mine = x < run;
-                // labels.  Diagonal: is_match(i, j), Option<u8> equality with None == None (sequence.rs:113-114); run cells lie in
-                // the window, so their characters are in s1w / s2w.  Gaps: open/extend from last_choice (algo.rs:373-379, 388-394).
-                const bool lab = diag & mine;
-                const int a = (lab && ci < m) ? (int)s1w[ci - s1w0] : -1;
-                const int b = (lab && cj < n) ? (int)s2w[cj - s2w0] : -1;
-                const uint32_t mmask = __ballot_sync(0xffffffffu, lab && a == b);
-                const uint32_t nm = (uint32_t)__popc(mmask);
-                const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
-                const bool opens = !diag && (last != ext);
-                const uint32_t gop = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
-                const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
-                if (mine) ops[nops + x] = (uint8_t)op;
-                n_match += nm;
-                n_mis += diag ? run - nm : 0u;
-                n_open += opens ? 1u : 0u;
-                n_ext += diag ? 0u : (opens ? run - 1u : run);
-                last = diag ? 0u : ext;
-                nops += run;
-                // last emitted cell, then the checked_sub move (algo.rs:412-417); run cells are all inside the table
-                end_i = i - (run - 1u) * di;
-                end_j = j - (run - 1u) * dj;
+                push(i, j, c0 | (run << 8));              // labels, counters and op stores happen in the emit warp
+                // the checked_sub move (algo.rs:412-417); run cells are all inside the table
                 const bool i_none = di && (i < run), j_none = dj && (j < run);
                 if (i_none && j_none) break;
                 i = i_none ? 0u : i - run * di;
@@ -293,27 +285,81 @@ __global__ void __launch_bounds__(32) gx_walk_kernel(const WalkParams P) {
                 if (i == 0 && j == 0) break;
                 // lane `run` looked at exactly (i, j) unless the run used all 32 lanes, the move was clamped, or that
                 // cell was outside the window (7): then look it up (and reload the window at the top of the loop).
-                // A warp-uniform branch: one lone warp runs the walk, so instructions issued are what an iteration
-                // costs, and the second lookup is a fifth of them.
+                // A warp-uniform branch: instructions issued are what an iteration costs.
                 if (run < 32u && !i_none && !j_none && c_next != 7u) c0 = c_next;
                 else c0 = cell_code(i, j);
             }
-            res.end_i = end_i;
-            res.end_j = end_j;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        if (P.debug) {
-            res.lcs_at_first_max = dbg_iters | (dbg_reloads << 32);
-            res.fill_ms = (double)(clock64() - dbg_t0);
-            res.walk_ms = (double)dbg_reload_cyc;
+        if (lane == 0) {
+            dbg[0] = dbg_iters | (dbg_reloads << 32);
+            dbg[1] = (unsigned long long)(clock64() - dbg_t0);
+            dbg[2] = (unsigned long long)dbg_reload_cyc;
         }
+        __syncwarp();
+        push(0u, 0u, 0xffffffffu);                        // end of path
+    } else {
+        // ================================================================ emit warp
+        uint8_t *ops = P.ops + pd->ops_off;
+        uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
+        uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
+        uint32_t end_i = i, end_j = j;
+        if (i == 0 && j == 0) {
+            // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
+            if (lane == 0) ops[0] = 0;
+            nops = 1;
+            n_match = 1;
+        }
+        uint32_t popped = 0;
+        for (;;) {
+            while (lds_volatile_u32(head) <= popped) {
+            }
+            const uint4 d = lds_volatile_uint4(ring + popped % WALK_RING);
+            __syncwarp();                                 // every lane has its copy: the slot may be reused
+            popped++;
+            if (lane == 0) sts_volatile_u32(tail, popped);
+            if (d.z == 0xffffffffu) break;
+            const uint32_t ri = d.x, rj = d.y, c0 = d.z & 3u, run = d.z >> 8;
+            const uint32_t x = (uint32_t)lane;
+            const bool diag = (c0 == 0u);
+            const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
+            const bool mine = x < run;
+            const uint32_t ci = ri - (mine ? x * di : 0u), cj = rj - (mine ? x * dj : 0u);
+            // labels.  Diagonal: is_match(i, j), Option<u8> equality with None == None (sequence.rs:113-114): the characters
+            // AFTER the cell's own (0-based s1[i], s2[j]; algo.rs:354).  Gaps: open/extend from last_choice (algo.rs:373-379, 388-394).
+            const bool lab = diag & mine;
+            const int a = (lab && ci < m) ? (int)__ldg(s1 + ci) : -1;
+            const int b = (lab && cj < n) ? (int)__ldg(s2 + cj) : -1;
+            const uint32_t mmask = __ballot_sync(0xffffffffu, lab && a == b);
+            const uint32_t nm = (uint32_t)__popc(mmask);
+            const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
+            const bool opens = !diag && (last != ext);
+            const uint32_t gop = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
+            const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
+            if (mine) ops[nops + x] = (uint8_t)op;
+            n_match += nm;
+            n_mis += diag ? run - nm : 0u;
+            n_open += opens ? 1u : 0u;
+            n_ext += diag ? 0u : (opens ? run - 1u : run);
+            last = diag ? 0u : ext;
+            nops += run;
+            end_i = ri - (run - 1u) * di;                 // last emitted cell
+            end_j = rj - (run - 1u) * dj;
+        }
+        res.end_i = end_i;
+        res.end_j = end_j;
         res.n_ops = nops;
         res.matches = n_match;
         res.mismatches = n_mis;
         res.gap_extensions = n_ext;
         res.opening_gaps = n_open;
+        if (P.debug) {
+            res.lcs_at_first_max = dbg[0];
+            res.fill_ms = (double)dbg[1];
+            res.walk_ms = (double)dbg[2];
+        }
+        if (lane == 0) P.results[q] = res;
     }
-    if (lane == 0) P.results[q] = res;
 }
 
 }  // namespace gx

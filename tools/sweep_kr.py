@@ -27,9 +27,10 @@ def workload(name):
     """-> (pairs as (blob, off1, len1, off2, len2), is_local, traceback)"""
     if name.startswith("corona"):
         seqs, jobs = wl.corona_pairs()
-        if name == "corona6":     # the 8-GPU shard of rank 0
+        shard = {"corona6": 8, "corona11": 4, "corona23": 2}.get(name)
+        if shard:                 # rank 0's shard of the 8 / 4 / 2-GPU run
             costs = [(len(seqs[a]) + 1) * (len(seqs[b]) + 1) for a, b in jobs]
-            jobs = [jobs[k] for k in wl.lpt_shards(costs, 8)[0]]
+            jobs = [jobs[k] for k in wl.lpt_shards(costs, shard)[0]]
         elif name == "corona1":
             jobs = jobs[:1]
         return gx.pack_pairs([(seqs[a], seqs[b]) for a, b in jobs]), False, True
@@ -49,6 +50,7 @@ def main():
     ap.add_argument("--combos", default="")
     ap.add_argument("--chain", default="0,1")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--batch", default="", help="comma list of GX_BATCH values (steps per hand-off batch) to force, e.g. 8,16,32")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_kr.jsonl"))
     args = ap.parse_args()
     combos = [tuple(int(x) for x in c.split("x")) for c in args.combos.split(",") if c] or ALL
@@ -60,12 +62,15 @@ def main():
         (blob, off1, len1, off2, len2), is_local, tb = workload(name)
         cells = int(((len1 + 1) * (len2 + 1)).sum())
         ref = None
-        for k, r in [(0, 0)] + combos:
+        batches = [int(b) for b in args.batch.split(",") if b] or [0]
+        for k, r, bsteps in [(0, 0, 0)] + [(k, r, b) for k, r in combos for b in batches]:
             for c in ([-1] if k == 0 else chains):
-                for var in ("GX_K", "GX_R", "GX_CHAIN1"):
+                for var in ("GX_K", "GX_R", "GX_CHAIN1", "GX_BATCH"):
                     os.environ.pop(var, None)
                 if k:
                     os.environ["GX_K"], os.environ["GX_R"], os.environ["GX_CHAIN1"] = str(k), str(r), str(c)
+                if bsteps:
+                    os.environ["GX_BATCH"] = str(bsteps)
                 try:
                     plan = gx.Plan(len1, len2, SCORES, is_local, traceback=tb)
                     plan.upload(blob, off1, off2)
@@ -80,6 +85,7 @@ def main():
                     wall = (time.perf_counter() - t0) / args.steps * 1e3
                     scores = plan.fetch_scores().tolist() if not tb else plan.fetch()[0]["score"].tolist()
                     rec = dict(workload=name, K=int(plan.stat(15)), R=int(plan.stat(19)), chain1=int(plan.stat(17)), forced=bool(k),
+                               batch=int(plan.stat(22)), resident=int(plan.stat(21)),
                                fill_ms=float(np.median(fills)), fill_min=float(min(fills)), walk_ms=float(np.median(walks)), wall_ms=wall,
                                gcups_fill=cells / (np.median(fills) * 1e-3) / 1e9, cells=cells)
                     if ref is None:
