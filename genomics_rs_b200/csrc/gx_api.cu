@@ -652,7 +652,10 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
     // is where the time goes (resident strips).  profiles/r2e_sweep_batch_*.jsonl.
     const uint32_t SPC = 64u / (uint32_t)(R * K), CPB_MAX = std::max(1u, 32u / (SPC * (uint32_t)R));
     {
-        uint32_t steps = pl->resident ? (K >= 16 ? 16u : 8u) : 32u;
+        // (measured after the batch length became a run-time parameter, profiles/r2f_sweep_shards_batch.jsonl: 32 steps is
+        // also as good or better for resident strips -- BRCA2 1.08 -> 1.00 ms, one 30 kb pair 2.93 -> 2.74 ms, the 6-pair shard
+        // 4.74 -> 4.69 ms -- so every plan uses the longest batch; GX_BATCH forces another length)
+        uint32_t steps = 32u;
         if (pl->tun.batch > 0) steps = (uint32_t)pl->tun.batch;
         uint32_t cpb = std::max(1u, steps / SPC);
         while (cpb & (cpb - 1)) cpb &= cpb - 1;          // power of two

@@ -19,7 +19,7 @@
 
 namespace gx {
 
-// dynamic shared memory of one walk CTA: a 1 KB control block (descriptor ring between the two warps, head / tail words,
+// dynamic shared memory of one walk CTA: a 1 KB control block (descriptor ring between the two warps, tail word,
 // debug counters) and two code-window buffers.
 // A window is 256 rows of one strip = 256/R (+1) row blocks + 31 steps of lane skew, 64/(R*K) steps per code chunk.
 __host__ __device__ constexpr uint32_t walk_chunks(int K, int R) { return (uint32_t)((256 / R + 1 + 31 + 64 / (R * K) - 1) / (64 / (R * K)) + 1); }
@@ -35,6 +35,9 @@ __device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *p) {
 }
 __device__ __forceinline__ void sts_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_volatile_uint4(uint4 *p, uint4 v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint4 lds_volatile_uint4(const uint4 *p) {
     uint4 v;
@@ -135,15 +138,15 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
     constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
     constexpr int NCH = (int)walk_chunks(K, R);           // code chunks per fill-lane in a window
     extern __shared__ __align__(16) uint8_t walk_smem[];
-    uint4 *ring = reinterpret_cast<uint4 *>(walk_smem);                                   // WALK_RING descriptors {i, j, code | run << 8, -}
-    uint32_t *head = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16);             // descriptors pushed (path warp)
-    uint32_t *tail = head + 1;                                                             // descriptors consumed (emit warp)
+    // descriptor ring, LL style: {i, j, code | run << 8, sequence number}.  One lane writes a descriptor with ONE 16-byte
+    // shared-memory store and the emit warp polls the slot until it carries the sequence number it expects: no head word,
+    // no fence on the path warp's dependent chain.  `tail` (descriptors consumed) is only read when the ring looks full.
+    uint4 *ring = reinterpret_cast<uint4 *>(walk_smem);
+    uint32_t *tail = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16);
     unsigned long long *dbg = reinterpret_cast<unsigned long long *>(walk_smem + WALK_RING * 16 + 16);
     uint8_t *bufs = walk_smem + WALK_CTRL_BYTES;
-    if (threadIdx.x == 0) {
-        sts_volatile_u32(head, 0u);
-        sts_volatile_u32(tail, 0u);
-    }
+    if (threadIdx.x < WALK_RING) ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);     // sequence numbers start at 1
+    if (threadIdx.x == 0) sts_volatile_u32(tail, 0u);
     __syncthreads();
 
     if (wid == 0) {
@@ -157,16 +160,17 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
         uint32_t np = 0xffffffffu, ns = 0, nr0 = 0, nr1 = 0;
         // current window: tile (wp, ws), local rows [wr0, wr1], first chunk wc0
         uint32_t wp = 0xffffffffu, ws = 0, wr0 = 0, wr1 = 0, wc0 = 0;
-        uint32_t pushed = 0;
+        uint32_t pushed = 0, tail_seen = 0;
         auto push = [&](uint32_t pi, uint32_t pj, uint32_t meta) __attribute__((always_inline)) {
-            if (lane == 0) {
-                while (pushed - lds_volatile_u32(tail) >= WALK_RING) {
-                }
-                ring[pushed % WALK_RING] = make_uint4(pi, pj, meta, 0u);
-                __threadfence_block();                       // descriptor before the head word
-                sts_volatile_u32(head, pushed + 1u);
+            if (pushed - tail_seen >= WALK_RING) {           // looks full: refresh the consumer's count (rare: the emit warp is faster)
+                do {
+                    tail_seen = lds_volatile_u32(tail);
+                } while (pushed - tail_seen >= WALK_RING);
             }
             pushed++;
+            // (the lap number rides in the top bits of the first half as well: a reader that caught the two 8-byte halves of the
+            // slot from different laps -- should 16-byte shared accesses ever be split -- does not accept it)
+            if (lane == 0) sts_volatile_uint4(ring + (pushed - 1u) % WALK_RING, make_uint4(pi | (((pushed >> 5) & 7u) << 29), pj, meta, pushed));
         };
 
         // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (a run must end before it)
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
             dbg[2] = (unsigned long long)dbg_reload_cyc;
         }
         __syncwarp();
+        __threadfence_block();                            // debug counters before the end marker
         push(0u, 0u, 0xffffffffu);                        // end of path
     } else {
         // ================================================================ emit warp
@@ -312,9 +317,11 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
         }
         uint32_t popped = 0;
         for (;;) {
-            while (lds_volatile_u32(head) <= popped) {
-            }
-            const uint4 d = lds_volatile_uint4(ring + popped % WALK_RING);
+            uint4 d;
+            do {
+                d = lds_volatile_uint4(ring + popped % WALK_RING);
+            } while (d.w != popped + 1u || (d.x >> 29) != (((popped + 1u) >> 5) & 7u));
+            d.x &= 0x1fffffffu;                           // row indices stay below 2^29 (gx_check_scores)
             __syncwarp();                                 // every lane has its copy: the slot may be reused
             popped++;
             if (lane == 0) sts_volatile_u32(tail, popped);
