@@ -988,7 +988,8 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
             pl->h2d_bytes += pl->n_pairs * 16;
         }
     } else {
-        // alphabet of the batch: with <= 4 distinct bytes the fill uses the shared-memory profile path
+        // alphabet of the batch: with <= 4 distinct bytes (and scores that fit a byte) the fill uses the one-hot / IDP.4A path:
+        // the sequences are re-encoded to SHIFT AMOUNTS 8 * symbol (gx_fill.cuh, run_batch)
         bool seen[256] = {false};
         int nsym = 0;
         uint8_t lut[256];
@@ -1010,15 +1011,24 @@ int gx_plan_upload(gx_plan *pl, const uint8_t *blob, uint64_t blob_len, const ui
                     const uint8_t ch = blob[x];
                     if (!seen[ch]) {
                         seen[ch] = true;
-                        if (nsym < 4) lut[ch] = (uint8_t)nsym;
+                        if (nsym < 4) lut[ch] = (uint8_t)(8 * nsym);
                         nsym++;
                     }
                 }
                 done_to = std::max(done_to, hi);
             }
         }
-        pl->prof = nsym <= 4 && pl->n_tiles > 0;
+        {
+            // both forms of the recurrence put (score - (h+g)) resp. the raw score into one signed byte
+            const long long hg = (long long)pl->sc.h + pl->sc.g;
+            const long long v[4] = {pl->sc.s_match - hg, pl->sc.s_mismatch - hg, pl->sc.s_match, pl->sc.s_mismatch};
+            bool fits = true;
+            for (long long x : v) fits = fits && x >= -128 && x <= 127;
+            pl->prof = nsym <= 4 && fits && pl->n_tiles > 0;
+        }
         if (pl->prof) {
+            for (int x = 0; x < 256; ++x)
+                if (lut[x] == 255) lut[x] = 0;   // bytes outside the pairs' segments (over-read slack): any valid shift amount
             if (!pl->d_lut) {
                 int rc = pool_alloc(c, 256, (void **)&pl->d_lut);
                 if (rc) return rc;

@@ -26,9 +26,8 @@ __host__ __device__ constexpr int warps_per_sm(int K) { return WARPS_PER_CTA * c
 // per-warp shared memory: s1 panel segment (+32: 16 B alignment slack in front, 16 B over-read behind),
 // the left-boundary in-ring and right-boundary out-ring (2 x 32 rows x 8 B each) and one mbarrier.
 constexpr int WARP_SMEM_S1 = PANEL_H + 32;
-constexpr int WARP_SMEM_PROF = WARP_SMEM_S1 + 512 + 512 + 16;   // offset of the match/mismatch profile
-// profile: 4 symbols x (32*K columns) x 4 B = K*512 bytes per warp
-__host__ __device__ constexpr int warp_smem_bytes(int K) { return WARP_SMEM_PROF + K * 512; }
+constexpr int WARP_SMEM_BYTES = WARP_SMEM_S1 + 512 + 512 + 16;
+__host__ __device__ constexpr int warp_smem_bytes(int /*K*/) { return WARP_SMEM_BYTES; }
 
 struct PairDesc {
     uint64_t s1_off, s2_off;   // byte offsets of the two sequences in the device blob

@@ -98,36 +98,15 @@ __host__ __device__ __forceinline__ uint32_t tile_batches(uint32_t rows, uint32_
 }
 
 // lane 0's left boundary comes from the in-ring, every other lane's from its left neighbour's registers: a predicated
-// shared-memory load over the shuffle result instead of LDS + 2 SEL (the selects would sit on the ALU pipe, 2/K per cell)
+// shared-memory load over the shuffle results instead of LDS + 2 SEL (the selects would sit on the ALU pipe, 2/K per
+// cell; ptxas turns this into a predicated LDS.64 + two predicated moves on the FMA pipe -- two scalar loads were tried
+// and still get the moves, because SHFL writes its destination late).
 __device__ __forceinline__ void lds_over_if(int &x, int &y, const uint2 *p, bool pred) {
     // (no memory clobber: the load depends on this step's shuffle results, which pins it behind the __syncwarp that
     // published the in-ring; a clobber would serialise it against every other shared-memory access of the step)
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0,%1}, [%2];\n\t}"
                  : "+r"(x), "+r"(y)
                  : "r"(smem_u32(p)), "r"((uint32_t)pred));
-}
-
-// One profile row (match/mismatch scores of one s1 symbol against this lane's K columns) from shared memory.
-// Layout per symbol: K >= 4: [k/4][lane][k%4] ints -> K/4 conflict-free LDS.128;  K = 2: [lane][2] ints -> one LDS.64.
-template <int K>
-__device__ __forceinline__ void prof_row(const uint8_t *prof_lane /* profile base + lane*min(16, 4K) */, int sym, int *dst) {
-    const uint8_t *row = prof_lane + sym * (K * 128);
-    if constexpr (K >= 4) {
-        const int4 *pp = reinterpret_cast<const int4 *>(row);
-#pragma unroll
-        for (int q = 0; q < K / 4; ++q) {
-            const int4 v = pp[q * 32];
-            dst[4 * q + 0] = v.x;
-            dst[4 * q + 1] = v.y;
-            dst[4 * q + 2] = v.z;
-            dst[4 * q + 3] = v.w;
-        }
-    } else {
-        static_assert(K == 2, "profile rows exist for K = 2, 4, 8, 16");
-        const int2 v = *reinterpret_cast<const int2 *>(row);
-        dst[0] = v.x;
-        dst[1] = v.y;
-    }
 }
 
 // One batch of BATCH systolic steps of one warp.
@@ -148,24 +127,26 @@ __device__ __forceinline__ void prof_row(const uint8_t *prof_lane /* profile bas
 // so a single warp has min(R,K)-fold instruction-level parallelism and the dependent chain of a step is R+K-1 cells
 // for R rows (the step latency is what a lone strip, and the ramp of a pair's strip pipeline, run at).
 //
-// Shared-memory fetches are software-pipelined (PIPE): the s1 characters are loaded two steps ahead, the profile rows
-// one step ahead; `c1a` / `subc` carry that state from step to step and batch to batch.
+// Match / mismatch score of a cell.  PROF (the batch uses at most 4 distinct symbols and the scores fit a byte): sequences
+// are staged as SHIFT AMOUNTS 8*symbol, a row's character becomes the one-hot word 1 << c1 (one SHF per row), a column's
+// four possible scores sit in the bytes of one register (prof4[k], built once per tile), and
+//     S = E_diag + score  =  IDP.4A(onehot, prof4[k], E_diag)
+// is ONE instruction on the FMA pipe -- the add it replaces -- with no profile in shared memory (round 1 fetched a
+// profile row with K/4 LDS.128 + an address IMAD per step).  Otherwise: compare path (ISETP + SEL per cell).
+// The s1 character of the NEXT step is fetched while this one runs (`c1a` carries it from step to step, batch to batch).
 template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool MASKED, bool PAD, bool CHAIN1, bool THRU = false>
 __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int (&c2)[K], int (&eo)[R], int (&io)[R], int &vd,
                                           int &best, int &best_r, const int g, const int hg, const int ap, const int bp,
                                           const uint32_t one, const uint8_t *s1base /* s1 row 0 of this tile */,
-                                          const uint8_t *prof_lane /* profile base + lane*16 */,
+                                          const int (&prof4)[K] /* PROF: byte s = score of symbol s against column k */,
                                           const uint2 *inr /* left-boundary (E,I) of this batch's rows */, uint2 *outring, uint4 *code_dst,
                                           const int t0, const int rows, const int lane, const int kvalid,
-                                          int (&subc)[R * K] /* PIPE+PROF: profile rows of the step about to run */,
-                                          int (&c1a)[R] /* PIPE: s1 characters LOOK-1 steps ahead */, const int cpb /* chunks in this batch */) {
+                                          int (&c1a)[R] /* s1 characters of the step about to run */, const int cpb /* chunks in this batch */) {
     using G = Geo<K, R>;
     constexpr int KB = G::KB;
-    constexpr bool PIPE = (R * K <= 16) && (K < 16);
-    constexpr int LOOK = PROF ? 2 : 1;      // PIPE: at step s the characters of step s+LOOK are fetched
     const bool lane0 = lane == 0;
     // s1 character of tile row r; rows outside the tile are clamped only where they can occur (masked batches) --
-    // an unmasked batch looks at most 2R bytes past the tile's rows, which the staging buffer's slack covers
+    // an unmasked batch looks at most R bytes past the tile's rows, which the staging buffer's slack covers
     auto s1char = [&](int r) __attribute__((always_inline)) -> int {
         if (MASKED) return (int)s1base[min(max(r, 0), rows - 1)];
         return (int)s1base[r];
@@ -189,40 +170,12 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
             bool act[R];
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) act[rr] = MASKED ? ((r0 + rr >= 0) && (r0 + rr < rows)) : true;
-            // ---- match/mismatch scores of the R x K cells
-            int sub[R * K];
-            if (PIPE) {
-                int c1[R];   // characters of THIS step (compare path only)
-                if (PROF) {
+            // ---- this step's s1 characters (fetched one step ago); fetch the next step's
+            int c1[R];
 #pragma unroll
-                    for (int x = 0; x < R * K; ++x) sub[x] = subc[x];
-                    // profile rows of the next step (characters fetched one step ago) ...
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr) prof_row<K>(prof_lane, c1a[rr], &subc[rr * K]);
-                } else {
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr) c1[rr] = c1a[rr];
-                }
-                // ... and the characters LOOK steps ahead
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) c1a[rr] = s1char(r0 + LOOK * R + rr);
-                if (!PROF) {
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-                        for (int k = 0; k < K; ++k) sub[rr * K + k] = (c1[rr] == c2[k]) ? ap : bp;
-                }
-            } else {
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    const int c1 = s1char(r0 + rr);
-                    if (PROF) {
-                        prof_row<K>(prof_lane, c1, &sub[rr * K]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) sub[rr * K + k] = (c1 == c2[k]) ? ap : bp;
-                    }
-                }
+            for (int rr = 0; rr < R; ++rr) {
+                c1[rr] = PROF ? (int)(1u << c1a[rr]) : c1a[rr];      // PROF: one-hot word of the symbol (shift amounts 0, 8, 16, 24)
+                c1a[rr] = s1char(r0 + R + rr);
             }
             // ---- the R x K cells, anti-diagonal by anti-diagonal
             int e_[R], i_[R], ed_[R], mh_[R], rowbest[R];
@@ -244,7 +197,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                         if (CHAIN1) {
                             In = LOCAL ? __viaddmax_s32_relu(i_[rr], g, mh_[rr]) : __viaddmax_s32(i_[rr], g, mh_[rr]);
                             Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                            const int Sh = ed_[rr] + sub[rr * K + k];
+                            const int Sh = PROF ? __dp4a(c1[rr], prof4[k], ed_[rr]) : ed_[rr] + ((c1[rr] == c2[k]) ? ap : bp);
                             const int Mh = __viaddmax_s32(Dn, hg, Sh);
                             En = __viaddmax_s32(In, hg, Mh);   // local: I' >= 0 keeps E >= h+g, i.e. V >= 0
                             if (THRU) mh_[rr] = (k < kvalid) ? Mh : mh_[rr];
@@ -255,7 +208,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                         } else {
                             In = LOCAL ? __viaddmax_s32_relu(i_[rr], g, e_[rr]) : __viaddmax_s32(i_[rr], g, e_[rr]);
                             Dn = LOCAL ? __viaddmax_s32_relu(du[k], g, eu[k]) : __viaddmax_s32(du[k], g, eu[k]);
-                            const int Sn = ed_[rr] + sub[rr * K + k];
+                            const int Sn = PROF ? __dp4a(c1[rr], prof4[k], ed_[rr]) : ed_[rr] + ((c1[rr] == c2[k]) ? ap : bp);
                             const int Vn = LOCAL ? __vimax3_s32_relu(In, Dn, Sn) : __vimax3_s32(In, Dn, Sn);
                             En = Vn + hg;
                             Skey = Sn;
@@ -342,7 +295,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
     uint2 *inring = reinterpret_cast<uint2 *>(wsm + WARP_SMEM_S1);   // 2 x BR entries (double-buffered by batch)
     uint2 *outring = inring + 64;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(outring + 64);
-    uint8_t *prof = wsm + WARP_SMEM_PROF;   // [4 symbols][K/4][32 lanes][4] ints (K = 2: [4][32][2]) = K*512 bytes
+    static_assert(WARP_SMEM_S1 + 2 * 64 * 8 + 16 == WARP_SMEM_BYTES, "per-warp shared-memory layout");
 
     // the s1 staging buffer starts out as valid symbols: unmasked batches prefetch up to 2R bytes past the rows the
     // TMA copy delivered (stale bytes of an earlier tile, or these zeros -- any symbol 0..3 indexes a real profile row)
@@ -416,26 +369,15 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
 #pragma unroll
             for (int k = 0; k < K; ++k) c2[k] = (k < kvalid) ? (int)__ldg(s2g + k) : 256;
         }
-        if (PROF) {
+        // PROF: the four possible scores of each column, one per byte (symbols are staged as shift amounts 0, 8, 16, 24;
+        // padding columns hold 256 and score `mismatch` against everything)
+        int prof4[K];
 #pragma unroll
-            for (int sym = 0; sym < 4; ++sym) {
-                if constexpr (K >= 4) {
+        for (int k = 0; k < K; ++k) {
+            uint32_t w = 0u;
 #pragma unroll
-                    for (int q = 0; q < K / 4; ++q) {
-                        int4 v;
-                        v.x = (c2[4 * q + 0] == sym) ? ap : bp;
-                        v.y = (c2[4 * q + 1] == sym) ? ap : bp;
-                        v.z = (c2[4 * q + 2] == sym) ? ap : bp;
-                        v.w = (c2[4 * q + 3] == sym) ? ap : bp;
-                        *reinterpret_cast<int4 *>(prof + sym * (K * 128) + q * 512 + lane * 16) = v;
-                    }
-                } else {
-                    int2 v;
-                    v.x = (c2[0] == sym) ? ap : bp;
-                    v.y = (c2[1] == sym) ? ap : bp;
-                    *reinterpret_cast<int2 *>(prof + sym * (K * 128) + lane * 8) = v;
-                }
-            }
+            for (int sym = 0; sym < 4; ++sym) w |= ((uint32_t)((c2[k] == 8 * sym) ? ap : bp) & 0xffu) << (8 * sym);
+            prof4[k] = PROF ? (int)w : 0;
         }
 
         // ---- top boundary of the tile: (E,D) of row i0 for this lane's columns
@@ -569,26 +511,11 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         }
         phase ^= 1u;
         const uint8_t *s1base = s1buf + delta;
-        const uint8_t *prof_lane = prof + lane * (K >= 4 ? 16 : 4 * K);
-        __syncwarp();   // profile stores visible to the whole warp
-        // software-pipelined shared-memory fetches (run_batch, PIPE): profile rows of step 0, characters LOOK-1 steps ahead
-        int subc[R * K], c1a[R];
-        {
-            constexpr bool PIPE = (R * K <= 16) && (K < 16);
-            constexpr int LOOK = PROF ? 2 : 1;
+        __syncwarp();
+        // the s1 characters of step 0 (run_batch fetches one step ahead)
+        int c1a[R];
 #pragma unroll
-            for (int x = 0; x < R * K; ++x) subc[x] = 0;
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) c1a[rr] = 0;
-            if (PIPE) {
-                if (PROF) {
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr) prof_row<K>(prof_lane, s1base[min(max(-lane * R + rr, 0), rows - 1)], &subc[rr * K]);
-                }
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) c1a[rr] = s1base[min(max((LOOK - 1 - lane) * R + rr, 0), rows - 1)];
-            }
-        }
+        for (int rr = 0; rr < R; ++rr) c1a[rr] = s1base[min(max(-lane * R + rr, 0), rows - 1)];
 
         // ---- batch loop.  The hand-off rings are double-buffered (the global load of batch bt+2's left boundary is in
         //      flight while batch bt computes), and every batch ends with: publish its finished right-boundary rows,
@@ -677,13 +604,13 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
                 if constexpr (!LOCAL && !CODES && TRACK == 0) {
                     if (thru)
                         run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                           one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                           (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
+                                                                                           one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                           (int)(B * bt), rows, lane, kvalid, c1a, cpb);
                 }
                 if (!thru)
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                        one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                        (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
+                                                                                        one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                        (int)(B * bt), rows, lane, kvalid, c1a, cpb);
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
@@ -695,8 +622,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
                     uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                 one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                 (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
+                                                                                 one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                 (int)(B * bt), rows, lane, kvalid, c1a, cpb);
                     if (!post(bt, outr)) dead = true;
                 }
             } else {
@@ -704,8 +631,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
                     uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                  one, s1base, prof_lane, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                  (int)(B * bt), rows, lane, kvalid, subc, c1a, cpb);
+                                                                                  one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                  (int)(B * bt), rows, lane, kvalid, c1a, cpb);
                     if (!post(bt, outr)) dead = true;
                 }
             }

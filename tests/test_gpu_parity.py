@@ -114,6 +114,20 @@ def test_local_all_zero_table(gx, oracle, k, r, chain1, monkeypatch):
                     _same(r, o, oracle, f"m={len(a)} n={len(b)} K={k} chain1={chain1}")
 
 
+@pytest.mark.parametrize("scores", [(120, -100, -20, -30), (127, -128, -1, 0), (60, -70, -50, -9), (-3, -7, -2, -4)])
+def test_score_byte_range_paths(gx, oracle, scores):
+    """4-letter batches score through one IDP.4A per cell when (score - (h+g)) fits a signed byte and through the compare
+    path otherwise: scorings on both sides of that edge (and an all-negative one) against the faithful oracle"""
+    rng = np.random.default_rng(sum(scores) & 0xffff)
+    pairs = [random_pair(rng, int(rng.integers(1, 90)), int(rng.integers(1, 90)), similar=bool(k % 2)) for k in range(120)]
+    pairs += [random_pair(rng, 300, 520), random_pair(rng, 4100, 140)]
+    for is_local in (False, True):
+        got = gx.align_batch(pairs, scores, is_local)
+        for (a, b), r in zip(pairs, got):
+            o = oracle.align_faithful(a, b, scores, is_local) if len(a) < 1000 else oracle.align_linear(a, b, scores, is_local)
+            _same(r, o, oracle, f"m={len(a)} n={len(b)} {scores} local={is_local}")
+
+
 @pytest.mark.parametrize("scores", [CONFIG_TOML, TEST_CONFIG, (2, -1, -1, 0), (5, -4, -3, -10), (1, 0, -1, -1), (3, 1, -2, -2)])
 def test_random_small_vs_faithful(gx, oracle, scores):
     rng = np.random.default_rng(hash(scores) & 0xffff)
