@@ -366,7 +366,13 @@ using namespace gx;
 // ================================================================================================
 extern "C" {
 
-const char *gx_version(void) { return "gxalign 0.1 (sm_100a)"; }
+const char *gx_version(void) {
+#ifdef GX_CHECKED
+    return "gxalign 0.2 (sm_100a, checked build: device-side bounds assertions)";
+#else
+    return "gxalign 0.2 (sm_100a)";
+#endif
+}
 
 const char *gx_strerror(int s) {
     switch (s) {
@@ -1190,6 +1196,8 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
         }
     }
     fp.pairs = pl->d_pairs;
+    fp.n_pairs = (uint32_t)pl->n_pairs;
+    fp.code_bytes = pl->code_bytes;
     fp.tiles = pl->d_tiles;
     fp.n_tiles = (uint32_t)pl->n_tiles;
     fp.pmax = 0;   // launch_fill switches to the [strip][panel] list when every strip gets a warp
@@ -1235,15 +1243,18 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
     wp.traceback = pl->traceback ? 1 : 0;
     wp.have_best = pl->track == 2 ? 1 : 0;
     wp.debug = pl->tun.walk_stats;
+    wp.check = pl->d_ctrl + 2;
+    wp.code_bytes = pl->code_bytes;
+    wp.ops_bytes = pl->ops_bytes;
     {
         int rc = launch_walk(pl, wp);
         if (rc) return rc;
         pl->launches++;
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
-    uint32_t abort_word = 0;
-    CK(cudaMemcpyAsync(&abort_word, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    uint32_t abort_word2 = 0;
+    uint32_t ctrl_words[2] = {0, 0};   // [0] abort word, [1] checked build: site of a failed bounds check
+    CK(cudaMemcpyAsync(ctrl_words, pl->d_ctrl + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t ctrl2[2] = {0, 0};
     if (pl->lcs) {
         // alignment_table's second return value: a score-only fill pass that tracks the FIRST maximum, then the LCS
         // length of the two prefixes that end there (gx_lcs.cuh)
@@ -1258,7 +1269,7 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
             int rc = launch_fill(pl, fq, 0, 3);
             if (rc) return rc;
             pl->launches++;
-            CK(cudaMemcpyAsync(&abort_word2, pl->d_ctrl + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(ctrl2, pl->d_ctrl + 1, 8, cudaMemcpyDeviceToHost, c->stream));
         }
         LcsParams lp;
         lp.blob = pl->d_blob;
@@ -1276,6 +1287,12 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
     }
     if (fp.stats) CK(cudaMemcpyAsync(pl->h_stats, pl->d_stats, 64, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    uint32_t abort_word = ctrl_words[0];
+    const uint32_t abort_word2 = ctrl2[0];
+    if (ctrl_words[1] || ctrl2[1]) {
+        g_err = "checked build: device bounds check failed at site " + std::to_string(ctrl_words[1] ? ctrl_words[1] : ctrl2[1]);
+        return GX_ERR_INTERNAL;
+    }
     if (pl->tun.test_abort && pl->resident && pl->retries == 0) abort_word = 1;   // test hook: exercise the ticket-mode retry
     if (abort_word || abort_word2) {
         g_err = "fill kernel aborted: a tile waited > SPIN_LIMIT polls for a dependency";

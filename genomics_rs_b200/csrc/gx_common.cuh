@@ -29,6 +29,19 @@ constexpr int WARP_SMEM_S1 = PANEL_H + 32;
 constexpr int WARP_SMEM_BYTES = WARP_SMEM_S1 + 512 + 512 + 16;
 __host__ __device__ constexpr int warp_smem_bytes(int /*K*/) { return WARP_SMEM_BYTES; }
 
+// Checked build (-DGX_CHECKED, `GX_BUILD_TAG=chk`): every shared-memory ring / staging index, code-chunk offset,
+// boundary-buffer row and op index the kernels form is range-checked on the device; a violation records its site number
+// in the plan's control block (word 2) and the execute returns GX_ERR_INTERNAL naming it.  compute-sanitizer is closed on
+// the B200 pool this was developed on; the GPU test-suite is run against this build instead (tools/gpu_checked.sh).
+#ifdef GX_CHECKED
+#define GX_CHECK(word, cond, site)                                   \
+    do {                                                             \
+        if (!(cond)) atomicMax(reinterpret_cast<unsigned int *>(word), (unsigned int)(site)); \
+    } while (0)
+#else
+#define GX_CHECK(word, cond, site) ((void)0)
+#endif
+
 struct PairDesc {
     uint64_t s1_off, s2_off;   // byte offsets of the two sequences in the device blob
     uint64_t colbuf_off;       // u64 entries: strip s (< S-1) right boundary column, row i (1..m) at colbuf_off + s*m + (i-1)
@@ -63,10 +76,11 @@ struct DevResult {
 
 struct FillParams {
     const uint8_t *blob;
-    const uint8_t *blob_sym;         // blob re-encoded to symbols 0..3 (profile path), else null
+    const uint8_t *blob_sym;         // blob re-encoded to shift amounts 8*symbol (one-hot / IDP.4A path), else null
     uint32_t one;                    // the constant 1, opaque to ptxas (keeps code-bit IMADs on the FMA pipe)
     const PairDesc *pairs;
     const TileDesc *tiles;
+    uint32_t n_pairs;                // pairs in `pairs` (checked build)
     uint32_t n_tiles;
     uint32_t pmax;                   // resident-strips mode: tiles are laid out [strip][panel] with pmax entries per strip; else 0
     uint32_t parity;                 // LL parity bit of this execute (SURVEY "boundary hand-off")
@@ -77,6 +91,7 @@ struct FillParams {
     unsigned long long *colbuf;
     int2 *top;
     uint8_t *codes;
+    uint64_t code_bytes;             // size of `codes` (checked build)
     int4 *tile_best;
     uint32_t pad_keys;               // 1: padded columns of a pair's last strip could reach the maximum (s_mismatch >= 0): mask their keys
     uint32_t poll_nap;               // ns a strip sleeps between two polls of its left boundary (0: poll back to back)
@@ -99,6 +114,8 @@ struct WalkParams {
     int kcols_log2;                  // log2(K) of the fill kernel that wrote the codes (informational; the walk is templated on K, R)
     int is_local, traceback, have_best;
     int debug;                       // GX_WALK_STATS: iterations/reloads/cycles returned in spare result fields
+    uint32_t *check;                 // checked build: where a failed bounds check records its site (control block word 2)
+    uint64_t code_bytes, ops_bytes;  // sizes of the codes / ops buffers (checked build)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -141,7 +141,8 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                                           const int (&prof4)[K] /* PROF: byte s = score of symbol s against column k */,
                                           const uint2 *inr /* left-boundary (E,I) of this batch's rows */, uint2 *outring, uint4 *code_dst,
                                           const int t0, const int rows, const int lane, const int kvalid,
-                                          int (&c1a)[R] /* s1 characters of the step about to run */, const int cpb /* chunks in this batch */) {
+                                          int (&c1a)[R] /* s1 characters of the step about to run */, const int cpb /* chunks in this batch */,
+                                          uint32_t *chk /* checked build: violation word */, const int s1lo, const int s1hi /* valid s1base indices */) {
     using G = Geo<K, R>;
     constexpr int KB = G::KB;
     const bool lane0 = lane == 0;
@@ -149,6 +150,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
     // an unmasked batch looks at most R bytes past the tile's rows, which the staging buffer's slack covers
     auto s1char = [&](int r) __attribute__((always_inline)) -> int {
         if (MASKED) return (int)s1base[min(max(r, 0), rows - 1)];
+        GX_CHECK(chk, r >= s1lo && r < s1hi, 11);
         return (int)s1base[r];
     };
 #pragma unroll 1
@@ -165,6 +167,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
             for (int rr = 0; rr < R; ++rr) {
                 el[rr] = __shfl_up_sync(FULL, eo[rr], 1);
                 il[rr] = __shfl_up_sync(FULL, io[rr], 1);
+                GX_CHECK(chk, step * R + rr >= 0 && step * R + rr < 32, 12);
                 lds_over_if(el[rr], il[rr], inr + step * R + rr, lane0);
             }
             bool act[R];
@@ -272,6 +275,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                     best = upd ? rowbest[rr] : best;
                     best_r = upd ? r0 + rr : best_r;
                 }
+                GX_CHECK(chk, step * R + rr < 32, 13);
                 if (lane == 31 && act[rr]) outring[step * R + rr] = make_uint2((uint32_t)e_[rr], (uint32_t)i_[rr]);   // row R*(t0+step-31)+rr
             }
         });
@@ -312,6 +316,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
     const uint32_t one = P.one;
     const uint32_t parity = P.parity;
     uint32_t *abort_word = P.ticket + 1;
+    uint32_t *chk = P.ticket + 2;        // checked build: site number of a failed bounds check
+    (void)chk;
     bool dead = false;
     const uint8_t *seq = PROF ? P.blob_sym : P.blob;   // PROF: sequences re-encoded to symbols 0..3 (gx_encode_kernel)
 
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         if (tk >= P.n_tiles) break;
         const TileDesc td = P.tiles[tk];
         if (td.pair == 0xffffffffu) break;      // padding: this strip has fewer panels
+        GX_CHECK(chk, td.pair < P.n_pairs, 1);
         const long long st_t0 = P.stats ? clock64() : 0;
         const unsigned long long tl_take = P.stats ? globaltimer_ns() : 0ull;
         unsigned long long tl_dp0 = 0ull;
@@ -350,6 +357,8 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         const int kvalid = min(max(n - jl, 0), K);
         const bool has_pad = (s + 1) * W > n;
         const int col0 = (int)pd->col0;
+        GX_CHECK(chk, p >= 0 && p < (int)pd->P && s >= 0 && s < S && rows > 0 && rows <= PANEL_H, 2);
+        GX_CHECK(chk, BR >= 1 && BR <= 32 && cpb >= 1 && cpb <= G::CPB_MAX, 3);
 
         // ---- stage s1[i0 .. i0+rows) with a TMA bulk copy (16-byte aligned window around it)
         const uint8_t *s1g = seq + pd->s1_off + i0;
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         unsigned long long nxt = 0;
         auto issue = [&](uint32_t bt) __attribute__((always_inline)) {
             const int r = (int)(BR * bt) + lane;
+            GX_CHECK(chk, !(has_left && lane < BR && r < rows) || (i0 + r >= 0 && i0 + r < m), 4);
             if (has_left && lane < BR && r < rows) nxt = ld_bnd(cb_in + r);
         };
         if (has_left && P.start_lead > 0) {
@@ -549,6 +559,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             uint2 cur;
             cur.x = has_left ? (uint32_t)nxt : (uint32_t)((LOCAL ? 0 : h + (i0 + rb + 1) * g) + hg);  // algo.rs:204-211: V = delete_score
             cur.y = has_left ? (uint32_t)(((int)(uint32_t)(nxt >> 32)) >> 1) : (uint32_t)NEG32;
+            GX_CHECK(chk, !lane_b || (b & 1u) * BR + lane < 64, 5);
             if (lane_b) inring[(b & 1u) * BR + lane] = cur;
             return true;
         };
@@ -560,6 +571,7 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         int pub_row = -1;
         auto flush_pub = [&]() __attribute__((always_inline)) {
             if (pub_row >= 0) {
+                GX_CHECK(chk, i0 + pub_row < m, 6);
                 const unsigned long long packed =
                     (unsigned long long)pub.x | ((unsigned long long)((pub.y << 1) | parity) << 32);
                 if (right_band) st_relaxed_sys_u64(cb_out + pub_row, packed);
@@ -601,16 +613,18 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
             for (; bt < m_end && !dead; ++bt) {
                 uint2 *outr = outring + (bt & 1u) * BR;
                 uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
                 if constexpr (!LOCAL && !CODES && TRACK == 0) {
                     if (thru)
                         run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                            one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                           (int)(B * bt), rows, lane, kvalid, c1a, cpb);
+                                                                                           (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
                 }
                 if (!thru)
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                         one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                        (int)(B * bt), rows, lane, kvalid, c1a, cpb);
+                                                                                        (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
@@ -621,18 +635,22 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
                 for (; bt < nb_body && !dead; ++bt) {
                     uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                  one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                 (int)(B * bt), rows, lane, kvalid, c1a, cpb);
+                                                                                 (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
                     if (!post(bt, outr)) dead = true;
                 }
             } else {
                 for (; bt < nb_body && !dead; ++bt) {
                     uint2 *outr = outring + (bt & 1u) * BR;
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
                     run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
                                                                                   one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                  (int)(B * bt), rows, lane, kvalid, c1a, cpb);
+                                                                                  (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
                     if (!post(bt, outr)) dead = true;
                 }
             }
@@ -644,8 +662,10 @@ __global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(co
         {
             int2 *tp = P.top + pd->top_off + jl;
 #pragma unroll
-            for (int k = 0; k < K; ++k)
+            for (int k = 0; k < K; ++k) {
+                GX_CHECK(chk, !(k < kvalid) || jl + k < n, 8);
                 if (k < kvalid) st_cg_int2(tp + k, make_int2(eu[k], du[k]));
+            }
             __syncwarp();
             if (lane == 0) st_release_u32(P.progress + pd->progress_off + s, (uint32_t)(p + 1));
         }

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
             const uint32_t t = r / R + l;                         // the step at which fill-lane l worked on this row's block
             const uint32_t bitpos = (((t % SPC) * R + r % R) * K + k) * 2;
             const uint32_t widx = inwin ? (((t / SPC - wc0) * 32 + l) * 4 + (bitpos >> 5)) : 0u;
+            GX_CHECK(P.check, widx < walk_buf_bytes(K, R) / 4, 21);
             const uint32_t word = reinterpret_cast<const uint32_t *>(win)[widx];
             uint32_t code = inwin ? ((word >> (bitpos & 31u)) & 3u) : 7u;
             code = (cj == 0u) ? bnd_col0 : code;                  // column 0: only delete_score is finite; local stops
@@ -207,6 +208,8 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
                     auto issue_codes = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) {
                         const uint32_t c0w = (r0 / R) / SPC;
                         const uint32_t nch = (r1 / R + 31) / SPC - c0w + 1;   // <= NCH
+                        GX_CHECK(P.check, nch <= (uint32_t)NCH && (uint64_t)(c0w + nch) * 512 <= pd->tile_code_bytes &&
+                                              pd->codes_off + (uint64_t)(p * pd->S + s_ + 1) * pd->tile_code_bytes <= P.code_bytes, 23);
                         const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
                                                                              (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
                                             (size_t)c0w * 32 + lane;
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
             const bool opens = !diag && (last != ext);
             const uint32_t gop = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
             const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
+            GX_CHECK(P.check, !mine || (nops + x <= m + n && pd->ops_off + nops + x < P.ops_bytes), 22);
             if (mine) ops[nops + x] = (uint8_t)op;
             n_match += nm;
             n_mis += diag ? run - nm : 0u;
