@@ -83,6 +83,10 @@ __device__ __forceinline__ void code_acc(uint32_t &cw, int S, int I, int V, uint
 // for plans that keep every warp slot busy, short ones where the pipeline ramp of a pair is what the time goes into
 // (profiles/r2e_sweep_batch_*.jsonl: 1 Mbp x 1 Mbp 322 -> 282 ms, 45 coronavirus pairs 17.9 -> 16.7 ms at 32 steps; one
 // BRCA2 pair 1.0 -> 1.4 ms).  At most 32 rows per batch: one boundary row per lane.
+// 8-warp CTAs per SM of the score-only instances (A/B switch: 3 = 24 warps at <= 85 registers)
+#ifndef GX_SCORE_CTAS
+#define GX_SCORE_CTAS 2
+#endif
 template <int K, int R>
 struct Geo {
     static_assert(R * K <= 64 && (R & (R - 1)) == 0 && (K & (K - 1)) == 0, "R x K cells must fit one 16-byte code chunk");
@@ -284,7 +288,7 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
 }
 
 template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
-__global__ void __launch_bounds__(CTA_THREADS, ctas_per_sm(K)) gx_fill_kernel(const FillParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE_CTAS) gx_fill_kernel(const FillParams P) {
     using G = Geo<K, R>;
     constexpr int W = G::W;
     const int cpb = (int)P.cpb;          // code chunks per hand-off batch (run-time: see Geo)
