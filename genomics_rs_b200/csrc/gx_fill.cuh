@@ -160,6 +160,10 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
 #pragma unroll 1
     for (int ch = 0; ch < cpb; ++ch) {
         uint32_t cw[4] = {0u, 0u, 0u, 0u};
+        // TRACK 2/3 (start cell / first maximum): the row maxima of this chunk's steps are kept in registers and folded into
+        // (best, best_r) AFTER the chunk.  Updating per step put a compare + two selects on predicates between the cells of
+        // consecutive steps and cost a lone strip 50 % (BRCA2 local fill 1.93 -> 1.30 ms, tools/mode_probe.py).
+        int rbk[(TRACK == 2 || TRACK == 3) ? G::SPC * R : 1];
         static_for<G::SPC>([&](auto uc) {
             constexpr int uu = decltype(uc)::value;
             const int step = ch * G::SPC + uu;          // step inside the batch
@@ -172,7 +176,15 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
                 el[rr] = __shfl_up_sync(FULL, eo[rr], 1);
                 il[rr] = __shfl_up_sync(FULL, io[rr], 1);
                 GX_CHECK(chk, step * R + rr >= 0 && step * R + rr < 32, 12);
+#ifdef GX_LDS_SEL
+                {   // A/B: the round-1 form -- unconditional load issued independently of the shuffles, then two selects
+                    const uint2 bnd = inr[step * R + rr];
+                    el[rr] = lane0 ? (int)bnd.x : el[rr];
+                    il[rr] = lane0 ? (int)bnd.y : il[rr];
+                }
+#else
                 lds_over_if(el[rr], il[rr], inr + step * R + rr, lane0);
+#endif
             }
             bool act[R];
 #pragma unroll
@@ -265,24 +277,28 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
             for (int rr = 0; rr < R; ++rr) {
                 eo[rr] = e_[rr];
                 io[rr] = i_[rr];
-                if (TRACK == 2) {
-                    // last maximum in row-major order wins (Iterator::max_by, algo.rs:311-322): a later row
-                    // replaces an equal value; inside the row the key's low bits prefer the larger column.
-                    const bool upd = act[rr] && ((rowbest[rr] | (K - 1)) >= best);
-                    best = upd ? rowbest[rr] : best;
-                    best_r = upd ? r0 + rr : best_r;
+                if (TRACK == 2 || TRACK == 3) {
+                    rbk[uu * R + rr] = act[rr] ? rowbest[rr] : INT32_MIN;     // INT32_MIN: no row here
                 } else if (TRACK == 1) {
                     best = act[rr] ? max(best, rowbest[rr]) : best;
-                } else if (TRACK == 3) {
-                    // only a strictly larger value replaces the running first maximum (rows arrive in increasing order)
-                    const bool upd = act[rr] && ((rowbest[rr] | (K - 1)) > (best | (K - 1)));
-                    best = upd ? rowbest[rr] : best;
-                    best_r = upd ? r0 + rr : best_r;
                 }
                 GX_CHECK(chk, step * R + rr < 32, 13);
                 if (lane == 31 && act[rr]) outring[step * R + rr] = make_uint2((uint32_t)e_[rr], (uint32_t)i_[rr]);   // row R*(t0+step-31)+rr
             }
         });
+        if (TRACK == 2 || TRACK == 3) {
+            // TRACK 2: the LAST maximum in row-major order wins (Iterator::max_by, algo.rs:311-322): a later row replaces an
+            // equal value; inside the row the key's low bits prefer the larger column.  TRACK 3: the FIRST maximum
+            // (alignment_table's max_cell, algo.rs:258-262): only a strictly larger value replaces (rows arrive in
+            // increasing order).  A slot without a row (INT32_MIN) never replaces anything.
+            const int rbase = (t0 + ch * G::SPC - lane) * R;
+#pragma unroll
+            for (int x = 0; x < G::SPC * R; ++x) {
+                const bool upd = (TRACK == 2) ? ((rbk[x] | (K - 1)) >= best && rbk[x] != INT32_MIN) : ((rbk[x] | (K - 1)) > (best | (K - 1)));
+                best = upd ? rbk[x] : best;
+                best_r = upd ? rbase + x : best_r;
+            }
+        }
         if (CODES) st_cs_uint4(code_dst + ch * 32, make_uint4(cw[0], cw[1], cw[2], cw[3]));
     }
 }
