@@ -152,8 +152,7 @@ def build_workload(name: str, rank: int, world: int, n_pairs: int):
         gold = {tuple(c["pair"]): c for c in g["corona"]}
         return dict(blob=blob, off1=off1, len1=len1, off2=off2, len2=len2, is_local=False, traceback=True,
                     cells=int(sum(costs[k] for k in mine)), scaling="strong", mode="traceback", gold=[gold[jobs[k]] for k in mine],
-                    desc="config 3: all-vs-all global NW of the 10 comparison_data coronavirus genomes (45 pairs, ~30 kb each), "
-                         "score + traceback, pairs dealt LPT over ranks")
+                    desc=CORONA_WHAT)
     if name in ("brca2_global", "brca2_local"):
         a, b = wl.brca2_pair()
         blob = np.frombuffer(a + b, np.uint8).copy()
@@ -206,6 +205,26 @@ def cpu_baseline_sample(march_native: bool = True, rows: int = 12000, threads: i
     return out
 
 
+def workload_config(name: str, what: str, cells_per_step: float) -> dict:
+    """`config` of the JSON line: the workload, identical in our arm and in the --impl reference arm"""
+    return {"workload": name, "what": what, "scores": dict(zip(("s_match", "s_mismatch", "g", "h"), SCORES)),
+            "cells_per_step": float(cells_per_step)}
+
+
+CORONA_WHAT = ("config 3: all-vs-all global NW of the 10 comparison_data coronavirus genomes (45 pairs, ~30 kb each), "
+               "score + traceback, pairs dealt LPT over ranks")
+
+
+def mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate cannot be built
     here) on the host cores.  The reference aligns ONE pair on ONE thread (no rayon in algo.rs); to use the host
@@ -218,7 +237,13 @@ def run_reference(args):
     so = gxo.build(march="native")
     ncpu = os.cpu_count() or 1
     threads = max(1, min(ncpu, 32))
+    # the largest prefix whose 48 B/cell tables fit a third of the free host memory with one aligner per thread
+    # (a full 30 kb pair is 43 GB and 42 s on one thread: profiles/r2_cpu_full_pair.json)
     rows = 4000
+    for cand in (12000, 8000, 6000):
+        if threads * (cand + 1) ** 2 * 48 / 1e9 <= mem_available_gb() / 3:
+            rows = cand
+            break
     seqs, jobs = wl.corona_pairs()
     work = [(seqs[a][:rows], seqs[b][:rows]) for a, b in jobs]
     work = (work * ((threads + len(work) - 1) // len(work)))[:threads]
@@ -244,7 +269,7 @@ def run_reference(args):
         "impl": "reference", "metric": "GCUPS (affine NW/SW, score+traceback)", "value": val, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "reference fixtures (comparison_data genomes, prefixes)",
-        "config": {"workload": "corona45 (bounded sample, CPU)", "sample": sample},
+        "config": workload_config("corona45", CORONA_WHAT, sum((len(seqs[a]) + 1) * (len(seqs[b]) + 1) for a, b in jobs)),
         "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -458,12 +483,12 @@ def run_plan_workload(env, args, name: str, steps: int, warmup: int, headline: b
             "dtype": "int32" if kind == 0 else "int16x2",
             "data": "reference fixtures (tests/golden/fasta, gz copies of comparison_data/test_data)"
             if name != "reads150" else "synthetic (splitmix64 reads, SURVEY 8d)",
-            "config": {"workload": name, "what": w["desc"], "scores": dict(zip(("s_match", "s_mismatch", "g", "h"), SCORES)),
-                       "cells_per_step": cells, "K": K,
-                       "l2": ("each step rewrites %.2f GB of traceback codes + boundary buffers, far above the 126 MB L2, so no "
-                              "step sees a warm cache" % (code_all / 1e9)) if code_all > 2e8 else
-                             ("inputs (%.2f GB) exceed L2" % (blob.size * env.world / 1e9)) if blob.size * env.world > 2e8 else
-                             "working set below L2: a 512 MB buffer is rewritten between the timed steps (L2 flush, outside the timed span)"},
+            "config": workload_config(name, w["desc"], cells),
+            "plan": {"K": K, "chain1": bool(chain1),
+                     "l2": ("each step rewrites %.2f GB of traceback codes + boundary buffers, far above the 126 MB L2, so no "
+                            "step sees a warm cache" % (code_all / 1e9)) if code_all > 2e8 else
+                           ("inputs (%.2f GB) exceed L2" % (blob.size * env.world / 1e9)) if blob.size * env.world > 2e8 else
+                           "working set below L2: a 512 MB buffer is rewritten between the timed steps (L2 flush, outside the timed span)"},
             "wall_ms_per_step": wall_step, "fill_ms_per_step": fill_step, "walk_ms_per_step": walk_step,
             "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_step_ms, "h2d_bytes_per_step": h2d_all,
                     "d2h_bytes_per_step": d2h_all, "api": "gx_align_batch" if w["traceback"] else "gx_score_batch"},
@@ -568,12 +593,12 @@ def run_banded(env, args, steps: int, warmup: int, headline: bool = False):
             "value": cells / (ms_step * 1e-3) / 1e9, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic (splitmix64 pair, SURVEY 8d: s2 = s1 with 1/32 substitutions)",
-            "config": {"workload": "nw1m", "what": f"config 5: one {n} x {n} global NW, score only; {world} column band(s), one per GPU; "
-                       "boundary columns handed over by peer stores inside the fill kernel (no collective on the data path)",
-                       "scores": dict(zip(("s_match", "s_mismatch", "g", "h"), SCORES)), "cells_per_step": cells, "K": K,
-                       "band_fill_ms": per_rank, "score": final_score, "score_matches_frozen_oracle": bool(full_ok),
-                       "l2": "each step streams %.1f GB of strip-boundary buffers (8 B per row per strip), far above the 126 MB L2"
-                             % (dev_bytes / 1e9)},
+            "config": workload_config("nw1m", f"config 5: one {n} x {n} global NW, score only; one column band per GPU; boundary columns "
+                                      "handed over by peer stores inside the fill kernel (no collective on the data path)", cells),
+            "plan": {"K": K, "chain1": bool(chain1), "bands": world, "band_fill_ms": per_rank, "score": final_score,
+                     "score_matches_frozen_oracle": bool(full_ok),
+                     "l2": "each step streams %.1f GB of strip-boundary buffers (8 B per row per strip), far above the 126 MB L2"
+                           % (dev_bytes / 1e9)},
             "wall_ms_per_step": ms_step, "fill_ms_per_step": fill_max,
             "e2e": {"value": cells / (e2e_step_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": float(2 * n + 104 * 1), "d2h_bytes_per_step": float(104 * world),
@@ -597,9 +622,8 @@ def slim(rec):
             "gpu_launches", "parity_ok", "band_parity", "parity", "roofline", "roofline_hbm", "roofline_link")
     out = {k: rec[k] for k in keep if k in rec and rec[k] is not None}
     out["what"] = rec["config"]["what"]
-    for k in ("K", "band_fill_ms", "score", "l2"):
-        if k in rec["config"]:
-            out[k] = rec["config"][k]
+    out["cells_per_step"] = rec["config"]["cells_per_step"]
+    out.update({k: v for k, v in rec.get("plan", {}).items()})
     return out
 
 
