@@ -446,6 +446,8 @@ def run_plan_workload(env, args, name: str, steps: int, warmup: int, headline: b
     kind = int(plan.stat(9))
     K, chain1 = int(plan.stat(15)), int(plan.stat(17))
     code_bytes = float(plan.stat(4))
+    code_frac = plan.stat(23) if plan.stat(23) > 0 else 1.0     # share of the cells whose tile writes direction codes (code band)
+    band_fallbacks = int(max(plan.stat(24), 0))
     plan.close()
     del pin_t, flush
 
@@ -467,13 +469,19 @@ def run_plan_workload(env, args, name: str, steps: int, warmup: int, headline: b
                                 {"note": "s16x2: two pairs per register, 6 ALU-pipe instructions per two cells"})
         else:
             alu = ALU_PER_CELL[w["mode"]] + (1 if chain1 else 0)
-            roof = alu_roofline(env, w["mode"], alu, my_cells, my_fill, "gx_fill_kernel", {"K": K, "chain1": bool(chain1)})
+            extra = {"K": K, "chain1": bool(chain1)}
+            if w["traceback"] and code_frac < 1.0:
+                # code band: only tiles near the table's diagonal run the 5-ALU traceback cell, the rest the 3-ALU score cell
+                alu = ALU_PER_CELL["global_score"] + (1 if chain1 else 0) + 2.0 * code_frac
+                extra.update({"code_cell_frac": code_frac, "band_fallbacks": band_fallbacks,
+                              "note": "ALU instructions per cell = 3 + 2 x the share of cells in code-writing tiles"})
+            roof = alu_roofline(env, w["mode"] if code_frac >= 1.0 else "mixed", alu, my_cells, my_fill, "gx_fill_kernel", extra)
         hbm = None
         if w["traceback"]:
             if env.world == 1:
                 roof["traffic"], roof["traffic_source"] = ncu_traffic(name)
-            roof["algorithmic_bytes"] = code_bytes     # 2-bit codes written once per cell
-            gbs = code_bytes / (my_fill * 1e-3) / 1e9
+            roof["algorithmic_bytes"] = code_bytes * code_frac    # 2-bit codes written once per cell of a code-writing tile
+            gbs = code_bytes * code_frac / (my_fill * 1e-3) / 1e9
             hbm = {"bound": "hbm", "achieved": gbs, "peak": env.peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / env.peaks["hbm_gbs"],
                    "what": "traceback codes written once per cell (0.25 B/cell)", "peak_source": env.peaks["source"]}
         out = {

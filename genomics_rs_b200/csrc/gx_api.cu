@@ -19,7 +19,7 @@
 namespace gx {
 
 static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
-static_assert(sizeof(PairDesc) == 104, "PairDesc layout");
+static_assert(sizeof(PairDesc) == 112, "PairDesc layout");
 static_assert(warp_smem_bytes(2) % 16 == 0 && warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
               "per-warp smem must keep 16 B alignment");
 
@@ -129,7 +129,7 @@ static void pool_free(Ctx *c, void *p) {
 // Debug / experiment switches.  The environment is read ONCE per plan (gx_plan_create) or per streamed
 // batch call, never on the execute path; -1 = not set.
 struct Tunables {
-    int r = -1, batch = -1;
+    int r = -1, batch = -1, code_band = -1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
         fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0, test_abort = 0;
 };
@@ -142,6 +142,7 @@ static Tunables read_tunables() {
     t.k = env_int("GX_K", -1);
     t.r = env_int("GX_R", -1);
     t.batch = env_int("GX_BATCH", -1);
+    t.code_band = env_int("GX_CODE_BAND", -1);   // 0: codes in every tile; > 0: half-width of the code band in columns
     t.chain1 = env_int("GX_CHAIN1", -1);
     t.tickets = getenv("GX_TICKETS") ? 1 : -1;
     t.resident = env_int("GX_RESIDENT", -1);
@@ -219,6 +220,10 @@ struct gx_plan {
     float fill_ms = 0, walk_ms = 0;
     int launches = 0;
     int retries = 0;                   // resident-strips executes that were repeated in ticket mode
+    bool code_band = false;            // global traceback plan: only tiles near the diagonal write direction codes
+    int band_fallbacks = 0;            // executes repeated with codes everywhere because a path left the band
+    uint32_t left_band = 0;            // walks of the last execute that needed a tile outside the band
+    double code_cell_frac = 1.0;       // share of the cells that lie in code-writing tiles
     uint64_t h2d_bytes = 0, d2h_bytes = 0, dev_bytes = 0;
     // band plans (gx_band_*): every "pair" is a column band of one wide table
     gx_band *band = nullptr;
@@ -695,6 +700,17 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
         pd.tile_code_bytes = interior ? tile_batches(rows_max, (uint32_t)R, BATCH) * CPB * 32 * 16 : 0;
         pd.col0 = band_col0 ? (uint32_t)band_col0[q] : 0u;
+        // code band: a global alignment's path runs along the scaled diagonal j = i*n/m (all 45 coronavirus pairs stay
+        // within 316 columns of it); default half-width 1024 + |m - n| columns, tiles further out skip the codes
+        pd.code_w = GX_CODE_ALL;
+        if (pl->traceback && !is_local && !band_col0 && interior && pl->tun.code_band != 0) {
+            const uint64_t dmn = m > n ? m - n : n - m;
+            const uint64_t cw = pl->tun.code_band > 0 ? (uint64_t)pl->tun.code_band : 1024 + dmn;
+            if (cw < (1ull << 31)) {
+                pd.code_w = (uint32_t)cw;
+                pl->code_band = true;
+            }
+        }
         if (interior) {
             colbuf += (uint64_t)(pd.S - 1) * m;
             top += n;
@@ -736,6 +752,21 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         }
     }
     pl->code_bytes = codes;
+    if (pl->code_band) {   // share of the cells whose tile writes codes (bench.py: ALU instructions per cell, bytes written)
+        double with = 0, all = 0;
+        for (uint64_t q = 0; q < n_pairs; ++q) {
+            const PairDesc &pd = pl->pairs[q];
+            for (uint32_t p2 = 0; p2 < pd.P; ++p2) {
+                const double rows = (double)std::min<uint64_t>(PANEL_H, pd.m - (uint64_t)p2 * PANEL_H);
+                for (uint32_t s2 = 0; s2 < pd.S; ++s2) {
+                    const double cols = (double)std::min<uint64_t>((uint64_t)W, pd.n - (uint64_t)s2 * W);
+                    all += rows * cols;
+                    if (tile_has_codes(&pd, p2, s2, (uint32_t)W)) with += rows * cols;
+                }
+            }
+        }
+        pl->code_cell_frac = all > 0 ? with / all : 1.0;
+    }
     pl->ops_bytes = ops;
     pl->colbuf_entries = colbuf;
     pl->top_entries = top;
@@ -1113,6 +1144,24 @@ int gx_plan_execute(gx_plan *pl) try {
         pl->colbuf_dirty = true;     // the aborted execute left the LL parity words in an unknown state
         rc = plan_execute_once(pl, &aborted);
     }
+    // A path left the code band (a walk needed a tile that wrote no codes): repeat with codes in every tile.  The band is
+    // an optimisation of where traceback pointers are STORED, never of what is computed, so this keeps every result exact;
+    // the time of the discarded attempt stays in fill_ms / walk_ms.
+    if (rc == GX_OK && pl->code_band && pl->left_band != 0) {
+        const float f0 = pl->fill_ms, w0 = pl->walk_ms;
+        const int l0 = pl->launches;
+        for (auto &pd : pl->pairs) pd.code_w = GX_CODE_ALL;
+        pl->code_band = false;
+        pl->code_cell_frac = 1.0;
+        pl->band_fallbacks++;
+        Ctx *c = pl->ctx;
+        CK(cudaMemcpyAsync(pl->d_pairs, pl->pairs.data(), pl->n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        rc = plan_execute_once(pl, &aborted);
+        pl->fill_ms += f0;
+        pl->walk_ms += w0;
+        pl->launches += l0;
+    }
     return rc;
 }
 GX_GUARD_END
@@ -1247,6 +1296,7 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
     wp.have_best = pl->track == 2 ? 1 : 0;
     wp.debug = pl->tun.walk_stats;
     wp.check = pl->d_ctrl + 2;
+    wp.left_band = pl->d_ctrl + 3;
     wp.code_bytes = pl->code_bytes;
     wp.ops_bytes = pl->ops_bytes;
     {
@@ -1255,8 +1305,8 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
         pl->launches++;
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
-    uint32_t ctrl_words[2] = {0, 0};   // [0] abort word, [1] checked build: site of a failed bounds check
-    CK(cudaMemcpyAsync(ctrl_words, pl->d_ctrl + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t ctrl_words[3] = {0, 0, 0};   // [0] abort word, [1] checked build: site of a failed bounds check, [2] walks outside the code band
+    CK(cudaMemcpyAsync(ctrl_words, pl->d_ctrl + 1, 12, cudaMemcpyDeviceToHost, c->stream));
     uint32_t ctrl2[2] = {0, 0};
     if (pl->lcs) {
         // alignment_table's second return value: a score-only fill pass that tracks the FIRST maximum, then the LCS
@@ -1304,6 +1354,7 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
         return GX_ERR_INTERNAL;
     }
     if (bd) bd->epoch++;
+    pl->left_band = ctrl_words[2];
     CK(cudaEventElapsedTime(&pl->fill_ms, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&pl->walk_ms, c->ev[1], c->ev[2]));
     if (pl->lcs) CK(cudaEventElapsedTime(&pl->lcs_ms, c->ev[2], c->ev[3]));
@@ -1455,6 +1506,8 @@ double gx_plan_stat(const gx_plan *pl, int what) {
         case 15: return (double)pl->K;
         case 19: return (double)pl->R;
         case 20: return (double)pl->retries;
+        case 23: return pl->code_cell_frac;
+        case 24: return (double)pl->band_fallbacks;
         case 22: return (double)(pl->cpb * (64u / (uint32_t)(pl->R * pl->K)));   // steps per hand-off batch
         case 21: return pl->resident ? 1.0 : 0.0;
         case 17: return pl->chain1 ? 1.0 : 0.0;

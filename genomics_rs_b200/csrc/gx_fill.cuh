@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
         uint4 *code_base = nullptr;
         if (CODES)
             code_base = reinterpret_cast<uint4 *>(P.codes + pd->codes_off + (uint64_t)(p * S + s) * pd->tile_code_bytes) + lane;
+        // code band (global plans): tiles away from the table's diagonal run the score-only cell and write no codes
+        bool tcodes = CODES;
+        if constexpr (CODES && !LOCAL) tcodes = tile_has_codes(pd, (uint32_t)p, (uint32_t)s, (uint32_t)W);
 
         // ---- left boundary prefetch (LL protocol): lanes 0..BR-1 fetch the entries of local rows BR*bt + lane
         unsigned long long nxt = 0;
@@ -627,6 +630,22 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
         // phase 0: masked head batches (all batches of a THRU tile), then the unmasked body; phase 1: masked tail.
         // (One copy of each batch variant in the code; nothing here may end up as an out-of-line call -- the DP
         // state lives in registers.)
+        // one batch, in the variant this tile needs: with direction codes, or -- a tile outside the code band of a global
+        // traceback plan -- the score-only cell (both variants live in the kernel; the choice is uniform per tile)
+        auto do_batch = [&](auto masked_c, auto pad_c, uint32_t b, uint2 *outr, uint4 *cdst) __attribute__((always_inline)) {
+            constexpr bool M = decltype(masked_c)::value, PD = decltype(pad_c)::value;
+            if constexpr (CODES && !LOCAL) {
+                if (!tcodes) {
+                    run_batch<K, R, LOCAL, false, TRACK, PROF, M, PD, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp, one, s1base, prof4,
+                                                                             inring + (b & 1u) * BR, outr, nullptr, (int)(B * b), rows, lane, kvalid,
+                                                                             c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                    return;
+                }
+            }
+            run_batch<K, R, LOCAL, CODES, TRACK, PROF, M, PD, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp, one, s1base, prof4,
+                                                                     inring + (b & 1u) * BR, outr, cdst, (int)(B * b), rows, lane, kvalid, c1a, cpb,
+                                                                     chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+        };
         uint32_t bt = 0;
         for (int ph = 0; ph < 2 && !dead; ++ph) {
             const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
@@ -641,10 +660,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
                                                                                            one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
                                                                                            (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
                 }
-                if (!thru)
-                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                        one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                        (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                if (!thru) do_batch(std::true_type{}, std::integral_constant<bool, (TRACK != 0)>{}, bt, outr, cdst);
                 if (!post(bt, outr)) dead = true;
             }
             if (ph != 0 || thru || dead) continue;
@@ -657,9 +673,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                 GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
                                          pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
-                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                 one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                 (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                    do_batch(std::false_type{}, std::true_type{}, bt, outr, cdst);
                     if (!post(bt, outr)) dead = true;
                 }
             } else {
@@ -668,9 +682,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
                     uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
                 GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
                                          pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
-                    run_batch<K, R, LOCAL, CODES, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                  one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                  (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                    do_batch(std::false_type{}, std::false_type{}, bt, outr, cdst);
                     if (!post(bt, outr)) dead = true;
                 }
             }

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
 
         unsigned long long dbg_iters = 0, dbg_reloads = 0;
         long long dbg_reload_cyc = 0;
+        bool left_band = false;
         const long long dbg_t0 = clock64();
         if (!(i == 0 && j == 0)) {
             uint32_t c0 = cell_code(i, j);
@@ -204,6 +205,12 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
                     const long long dbg_r0 = P.debug ? clock64() : 0;
                     const uint32_t jj = j - 1, ii = i - 1;
                     const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
+                    // code band: a tile away from the table's diagonal holds no codes.  The path has left the band: give
+                    // up -- the host repeats the execute with codes everywhere (exactness never depends on the band).
+                    if (!tile_has_codes(pd, tp, ts, G::W)) {
+                        left_band = true;
+                        break;
+                    }
                     // copies of `nch` chunks of tile (p, s) starting at chunk c0w into buffer b (asynchronous)
                     auto issue_codes = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) {
                         const uint32_t c0w = (r0 / R) / SPC;
@@ -267,6 +274,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
                                 nr0 = PANEL_H - WR;
                             }
                         }
+                        if (np != 0xffffffffu && !tile_has_codes(pd, np, ns, G::W)) np = 0xffffffffu;   // nothing to prefetch there
                         if (np != 0xffffffffu) issue_codes(cb ^ 1u, np, ns, nr0, nr1);
                     }
                     if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        if (left_band && lane == 0) atomicAdd(P.left_band, 1u);
         if (lane == 0) {
             dbg[0] = dbg_iters | (dbg_reloads << 32);
             dbg[1] = (unsigned long long)(clock64() - dbg_t0);

@@ -234,6 +234,40 @@ def test_resident_abort_falls_back_to_tickets(gx, oracle, monkeypatch):
     plan.close()
 
 
+def test_code_band_and_fallback(gx, oracle, monkeypatch):
+    """global traceback plans write direction codes only near the table's diagonal; a path that leaves the band makes the
+    execute repeat with codes everywhere -- results are exact either way.  Pairs with a long terminal gap / big indels
+    against a forced 64-column band (fallback must fire), the same pairs with the default band and with the band off."""
+    rng = np.random.default_rng(99)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    a = lut[rng.integers(0, 4, size=9000)]
+    b1 = np.concatenate([a[:3000], a[4500:]])                                    # one 1500-base deletion
+    b2 = np.concatenate([lut[rng.integers(0, 4, size=2500)], a])                 # 2500 unrelated leading bases
+    b3 = a.copy(); b3[rng.choice(9000, 300, replace=False)] = lut[rng.integers(0, 4, size=300)]   # substitutions only
+    pairs = [(a, b1), (a, b2), (a, b3), (b1, a), (a[:5000], a[200:5300])]
+    exp = [oracle.align_linear(x, y, CONFIG_TOML, False) for x, y in pairs]
+    blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+    for band, want_fallback in (("64", True), (None, None), ("0", False)):
+        if band is None:
+            monkeypatch.delenv("GX_CODE_BAND", raising=False)
+        else:
+            monkeypatch.setenv("GX_CODE_BAND", band)
+        plan = gx.Plan(len1, len2, CONFIG_TOML, False, traceback=True)
+        plan.upload(blob, off1, off2)
+        for _ in range(2):
+            plan.execute()
+            res, ops, ops_off = plan.fetch()
+            for q, o in enumerate(exp):
+                assert res["score"][q] == o.score and res["n_ops"][q] == len(o.ops), (band, q)
+                assert np.array_equal(ops[int(ops_off[q]):int(ops_off[q]) + len(o.ops)], o.ops), (band, q)
+        if want_fallback is not None:
+            assert (plan.stat(24) >= 1) == want_fallback, (band, plan.stat(24))
+        if band == "0":
+            assert plan.stat(23) == 1.0
+        plan.close()
+    monkeypatch.delenv("GX_CODE_BAND", raising=False)
+
+
 def test_corona_all_vs_all(gx, oracle, goldens):
     """BASELINE config 3: 45 pairs of ~30 kb genomes, global, score + traceback, one batch."""
     order = goldens["corona_order"]
