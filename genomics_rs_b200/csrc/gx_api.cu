@@ -19,7 +19,7 @@
 namespace gx {
 
 static_assert(sizeof(DevResult) == sizeof(gx_result), "DevResult must mirror gx_result");
-static_assert(sizeof(PairDesc) == 112, "PairDesc layout");
+static_assert(sizeof(PairDesc) == 104, "PairDesc layout");
 static_assert(warp_smem_bytes(2) % 16 == 0 && warp_smem_bytes(4) % 16 == 0 && warp_smem_bytes(8) % 16 == 0 && warp_smem_bytes(16) % 16 == 0,
               "per-warp smem must keep 16 B alignment");
 
@@ -220,7 +220,8 @@ struct gx_plan {
     float fill_ms = 0, walk_ms = 0;
     int launches = 0;
     int retries = 0;                   // resident-strips executes that were repeated in ticket mode
-    bool code_band = false;            // global traceback plan: only tiles near the diagonal write direction codes
+    bool code_band = false;            // global traceback plan in ticket mode: only tiles near the diagonal write direction codes
+    uint8_t *d_tile_codes = nullptr;   // one flag per tile (indexed like tile_best)
     int band_fallbacks = 0;            // executes repeated with codes everywhere because a path left the band
     uint32_t left_band = 0;            // walks of the last execute that needed a tile outside the band
     double code_cell_frac = 1.0;       // share of the cells that lie in code-writing tiles
@@ -277,7 +278,9 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     Ctx *c = pl->ctx;
     const int K = pl->K;
     const bool L = pl->is_local != 0, C = pl->traceback;
+    const bool banded = pl->code_band && track_override < 0 && C && !L;   // two-variant kernel + per-tile flags
     FillKernel kern = (track_override >= 0) ? pick_fill(K, pl->R, pl->prof, pl->chain1, L, false, track_override)
+                      : banded              ? pick_fill(K, pl->R, pl->prof, pl->chain1, false, true, 4)
                                             : pick_fill(K, pl->R, pl->prof, pl->chain1, L, C, pl->track);
     if (!kern) {
         g_err = "no fill kernel for this (K, R)";
@@ -296,6 +299,7 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
     occ = std::min(occ, (codes_kernel ? warps_per_sm(K) : GX_SCORE_CTAS * WARPS_PER_CTA) / wpc);
     uint64_t cap = (uint64_t)c->sm_count * occ;
     FillParams fq = fp;
+    fq.tile_codes = banded ? pl->d_tile_codes : nullptr;
     if (pl->resident && pl->n_strips > cap) {
         g_err = "resident-strips plan does not fit the device (fewer than 16 single-warp CTAs per SM)";
         return GX_ERR_INTERNAL;
@@ -360,7 +364,7 @@ static int check_scores_impl(gx_scores sc, uint64_t m, uint64_t n, bool local) {
 
 static void plan_release(gx_plan *pl) {
     Ctx *c = pl->ctx;
-    void *ptrs[] = {pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_strips, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best, pl->d_first, pl->d_masks, pl->d_carry,
+    void *ptrs[] = {pl->d_tile_codes, pl->d_blob, pl->d_blob_sym, pl->d_lut, pl->d_stats, pl->d_timeline, pl->d_pairs, pl->d_tiles, pl->d_strips, pl->d_ctrl, pl->d_colbuf, pl->d_top, pl->d_codes, pl->d_best, pl->d_first, pl->d_masks, pl->d_carry,
                     pl->d_results, pl->d_ops, pl->d_off1, pl->d_off2, pl->d_len1, pl->d_len2, pl->d_scores};
     for (void *p : ptrs) pool_free(c, p);
 }
@@ -700,17 +704,6 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         const uint32_t rows_max = (uint32_t)std::min<uint64_t>(m, PANEL_H);
         pd.tile_code_bytes = interior ? tile_batches(rows_max, (uint32_t)R, BATCH) * CPB * 32 * 16 : 0;
         pd.col0 = band_col0 ? (uint32_t)band_col0[q] : 0u;
-        // code band: a global alignment's path runs along the scaled diagonal j = i*n/m (all 45 coronavirus pairs stay
-        // within 316 columns of it); default half-width 1024 + |m - n| columns, tiles further out skip the codes
-        pd.code_w = GX_CODE_ALL;
-        if (pl->traceback && !is_local && !band_col0 && interior && pl->tun.code_band != 0) {
-            const uint64_t dmn = m > n ? m - n : n - m;
-            const uint64_t cw = pl->tun.code_band > 0 ? (uint64_t)pl->tun.code_band : 1024 + dmn;
-            if (cw < (1ull << 31)) {
-                pd.code_w = (uint32_t)cw;
-                pl->code_band = true;
-            }
-        }
         if (interior) {
             colbuf += (uint64_t)(pd.S - 1) * m;
             top += n;
@@ -752,21 +745,6 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         }
     }
     pl->code_bytes = codes;
-    if (pl->code_band) {   // share of the cells whose tile writes codes (bench.py: ALU instructions per cell, bytes written)
-        double with = 0, all = 0;
-        for (uint64_t q = 0; q < n_pairs; ++q) {
-            const PairDesc &pd = pl->pairs[q];
-            for (uint32_t p2 = 0; p2 < pd.P; ++p2) {
-                const double rows = (double)std::min<uint64_t>(PANEL_H, pd.m - (uint64_t)p2 * PANEL_H);
-                for (uint32_t s2 = 0; s2 < pd.S; ++s2) {
-                    const double cols = (double)std::min<uint64_t>((uint64_t)W, pd.n - (uint64_t)s2 * W);
-                    all += rows * cols;
-                    if (tile_has_codes(&pd, p2, s2, (uint32_t)W)) with += rows * cols;
-                }
-            }
-        }
-        pl->code_cell_frac = all > 0 ? with / all : 1.0;
-    }
     pl->ops_bytes = ops;
     pl->colbuf_entries = colbuf;
     pl->top_entries = top;
@@ -788,7 +766,39 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         A((size_t)n_pairs * 2 * pl->carry_words * 4 + 16, (void **)&pl->d_carry);
     }
     A(n_pairs * sizeof(DevResult), (void **)&pl->d_results);
+    // code band (see gx_common.cuh): global traceback plans in ticket mode.  A global alignment's path runs along the scaled
+    // diagonal j = i*n/m (all 45 coronavirus pairs stay within 316 columns of it): default half-width 1024 + |m - n| columns.
+    // Resident-strips plans keep codes everywhere: their strips run as lone warps, which the two-variant kernel slows down.
+    std::vector<uint8_t> tile_codes;
+    if (pl->traceback && !is_local && !band_col0 && !pl->resident && pl->tun.code_band != 0 && best > 0) {
+        tile_codes.assign(best, 1);
+        double with = 0, all = 0;
+        for (uint64_t q = 0; q < n_pairs; ++q) {
+            const PairDesc &pd = pl->pairs[q];
+            const uint64_t dmn = pd.m > pd.n ? pd.m - pd.n : pd.n - pd.m;
+            const uint64_t cw = pl->tun.code_band > 0 ? (uint64_t)pl->tun.code_band : 1024 + dmn;
+            for (uint32_t p2 = 0; p2 < pd.P; ++p2) {
+                const double rows = (double)std::min<uint64_t>(PANEL_H, pd.m - (uint64_t)p2 * PANEL_H);
+                for (uint32_t s2 = 0; s2 < pd.S; ++s2) {
+                    const double cols = (double)std::min<uint64_t>((uint64_t)W, pd.n - (uint64_t)s2 * W);
+                    const bool in = tile_in_code_band(pd.m, pd.n, p2, s2, (uint32_t)W, cw);
+                    tile_codes[pd.tile_base + (uint64_t)p2 * pd.S + s2] = in ? 1 : 0;
+                    all += rows * cols;
+                    if (in) with += rows * cols;
+                }
+            }
+        }
+        pl->code_cell_frac = all > 0 ? with / all : 1.0;
+        pl->code_band = pl->code_cell_frac < 0.9;     // not worth a second kernel variant otherwise
+        if (!pl->code_band) pl->code_cell_frac = 1.0;
+        if (pl->code_band) A(best, (void **)&pl->d_tile_codes);
+    }
     if (pl->traceback) A(ops, (void **)&pl->d_ops);
+    if (rc == GX_OK && pl->code_band) {
+        cudaError_t e = cudaMemcpyAsync(pl->d_tile_codes, tile_codes.data(), best, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "upload tile code flags");
+    }
     if (rc == GX_OK && (!tiles.empty() || !strips.empty())) {
         cudaError_t e = cudaSuccess;
         if (!tiles.empty()) e = cudaMemcpyAsync(pl->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream);
@@ -1150,13 +1160,9 @@ int gx_plan_execute(gx_plan *pl) try {
     if (rc == GX_OK && pl->code_band && pl->left_band != 0) {
         const float f0 = pl->fill_ms, w0 = pl->walk_ms;
         const int l0 = pl->launches;
-        for (auto &pd : pl->pairs) pd.code_w = GX_CODE_ALL;
         pl->code_band = false;
         pl->code_cell_frac = 1.0;
         pl->band_fallbacks++;
-        Ctx *c = pl->ctx;
-        CK(cudaMemcpyAsync(pl->d_pairs, pl->pairs.data(), pl->n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
         rc = plan_execute_once(pl, &aborted);
         pl->fill_ms += f0;
         pl->walk_ms += w0;
@@ -1297,6 +1303,7 @@ static int plan_execute_once(gx_plan *pl, bool *aborted) {
     wp.debug = pl->tun.walk_stats;
     wp.check = pl->d_ctrl + 2;
     wp.left_band = pl->d_ctrl + 3;
+    wp.tile_codes = pl->code_band ? pl->d_tile_codes : nullptr;
     wp.code_bytes = pl->code_bytes;
     wp.ops_bytes = pl->ops_bytes;
     {

@@ -61,23 +61,20 @@ struct PairDesc {
     // flow control of a remote outbox: the consumer stores the number of executes it has finished here (our memory);
     // execute e may overwrite the consumer's inbox only once *ack >= e-1.  Null when the outbox is local or absent.
     const uint32_t *ack;
-    // Code band (global traceback plans): direction codes are only WRITTEN by tiles within `code_w` columns of the table's
-    // scaled diagonal j = i*n/m -- where the path of a global alignment runs; every other tile runs the score-only cell
-    // (5 instead of 9 instructions).  The walk verifies that every tile it enters has codes; if a path ever leaves the band
-    // the execute is repeated with codes everywhere (gx_plan_execute), so results stay exact.  GX_CODE_ALL = no band.
-    uint32_t code_w;
-    uint32_t pad_;
 };
-constexpr uint32_t GX_CODE_ALL = 0xffffffffu;
 
-// does tile (p, s) of this pair write / hold direction codes?  (same arithmetic in the fill and in the walk)
-__host__ __device__ __forceinline__ bool tile_has_codes(const PairDesc *pd, uint32_t p, uint32_t s, uint32_t W) {
-    if (pd->code_w == GX_CODE_ALL) return true;
+// Code band (global traceback plans in ticket mode): direction codes are only WRITTEN by tiles within `code_w` columns of
+// the table's scaled diagonal j = i*n/m -- where the path of a global alignment runs; every other tile runs the score-only
+// cell (5 instead of 9 instructions).  One flag byte per tile (FillParams / WalkParams::tile_codes, indexed like tile_best;
+// null = every tile has codes), written by the host, read by the fill (which variant to run) and by the walk, which
+// verifies that every tile it enters has codes; if a path ever leaves the band the execute is repeated with codes
+// everywhere (gx_plan_execute), so results stay exact.
+__host__ inline bool tile_in_code_band(uint64_t m, uint64_t n, uint32_t p, uint32_t s, uint32_t W, uint64_t code_w) {
     const uint64_t i0 = (uint64_t)p << PANEL_H_LOG2;
-    const uint64_t i1 = (i0 + PANEL_H < pd->m) ? i0 + PANEL_H : pd->m;
-    const uint64_t lo = i0 * pd->n / pd->m, hi = i1 * pd->n / pd->m;     // diagonal columns at the tile's first / last row
-    const uint64_t c0 = (uint64_t)s * W, c1 = c0 + W;                   // the tile's columns [c0, c1)
-    return c1 + pd->code_w > lo && c0 < hi + pd->code_w + 1;
+    const uint64_t i1 = (i0 + PANEL_H < m) ? i0 + PANEL_H : m;
+    const uint64_t lo = i0 * n / m, hi = i1 * n / m;     // diagonal columns at the tile's first / last row
+    const uint64_t c0 = (uint64_t)s * W, c1 = c0 + W;   // the tile's columns [c0, c1)
+    return c1 + code_w > lo && c0 < hi + code_w + 1;
 }
 
 struct TileDesc {
@@ -108,6 +105,7 @@ struct FillParams {
     unsigned long long *colbuf;
     int2 *top;
     uint8_t *codes;
+    const uint8_t *tile_codes;       // code band: one flag per tile (1 = this tile writes codes), or null (all do)
     uint64_t code_bytes;             // size of `codes` (checked build)
     int4 *tile_best;
     uint32_t pad_keys;               // 1: padded columns of a pair's last strip could reach the maximum (s_mismatch >= 0): mask their keys
@@ -132,6 +130,7 @@ struct WalkParams {
     int is_local, traceback, have_best;
     int debug;                       // GX_WALK_STATS: iterations/reloads/cycles returned in spare result fields
     uint32_t *left_band;             // control block word 3: walks that needed a tile outside the code band
+    const uint8_t *tile_codes;       // code band: one flag per tile, or null (every tile has codes)
     uint32_t *check;                 // checked build: where a failed bounds check records its site (control block word 2)
     uint64_t code_bytes, ops_bytes;  // sizes of the codes / ops buffers (checked build)
 };

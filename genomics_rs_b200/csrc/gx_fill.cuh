@@ -303,7 +303,10 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
     }
 }
 
-template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1>
+// BAND (global traceback plans in ticket mode): the kernel carries BOTH the traceback and the score-only batch variants and
+// picks per tile (FillParams::tile_codes).  A separate instantiation on purpose: a lone warp (resident strips) runs the
+// traceback variant 40 % slower when the second variant is compiled into the same kernel (BRCA2 fill 0.99 -> 1.41 ms).
+template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1, bool BAND = false>
 __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE_CTAS) gx_fill_kernel(const FillParams P) {
     using G = Geo<K, R>;
     constexpr int W = G::W;
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
             code_base = reinterpret_cast<uint4 *>(P.codes + pd->codes_off + (uint64_t)(p * S + s) * pd->tile_code_bytes) + lane;
         // code band (global plans): tiles away from the table's diagonal run the score-only cell and write no codes
         bool tcodes = CODES;
-        if constexpr (CODES && !LOCAL) tcodes = tile_has_codes(pd, (uint32_t)p, (uint32_t)s, (uint32_t)W);
+        if constexpr (BAND) tcodes = P.tile_codes[pd->tile_base + p * S + s] != 0;
 
         // ---- left boundary prefetch (LL protocol): lanes 0..BR-1 fetch the entries of local rows BR*bt + lane
         unsigned long long nxt = 0;
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
         // traceback plan -- the score-only cell (both variants live in the kernel; the choice is uniform per tile)
         auto do_batch = [&](auto masked_c, auto pad_c, uint32_t b, uint2 *outr, uint4 *cdst) __attribute__((always_inline)) {
             constexpr bool M = decltype(masked_c)::value, PD = decltype(pad_c)::value;
-            if constexpr (CODES && !LOCAL) {
+            if constexpr (BAND) {
                 if (!tcodes) {
                     run_batch<K, R, LOCAL, false, TRACK, PROF, M, PD, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp, one, s1base, prof4,
                                                                              inring + (b & 1u) * BR, outr, nullptr, (int)(B * b), rows, lane, kvalid,

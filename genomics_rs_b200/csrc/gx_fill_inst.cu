@@ -15,6 +15,7 @@ static FillKernel pick_mode(bool L, bool C, int track) {
     constexpr int K = GX_INST_K;
     constexpr int R = GX_INST_R;
     constexpr bool CH = GX_INST_CHAIN != 0;
+    if (track == 4) return gx_fill_kernel<K, R, false, true, 0, PROF, CH, true>;   // global traceback with a code band
     if (track == 3) {   // first-maximum pass of GX_FLAG_LCS_AT_MAX: score only
         if (L) return gx_fill_kernel<K, R, true, false, 3, PROF, CH>;
         return gx_fill_kernel<K, R, false, false, 3, PROF, CH>;

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
                     const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
                     // code band: a tile away from the table's diagonal holds no codes.  The path has left the band: give
                     // up -- the host repeats the execute with codes everywhere (exactness never depends on the band).
-                    if (!tile_has_codes(pd, tp, ts, G::W)) {
+                    if (P.tile_codes && P.tile_codes[pd->tile_base + tp * pd->S + ts] == 0) {
                         left_band = true;
                         break;
                     }
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
                                 nr0 = PANEL_H - WR;
                             }
                         }
-                        if (np != 0xffffffffu && !tile_has_codes(pd, np, ns, G::W)) np = 0xffffffffu;   // nothing to prefetch there
+                        if (np != 0xffffffffu && P.tile_codes && P.tile_codes[pd->tile_base + np * pd->S + ns] == 0)
+                            np = 0xffffffffu;   // nothing to prefetch there
                         if (np != 0xffffffffu) issue_codes(cb ^ 1u, np, ns, nr0, nr1);
                     }
                     if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;

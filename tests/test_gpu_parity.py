@@ -247,6 +247,7 @@ def test_code_band_and_fallback(gx, oracle, monkeypatch):
     pairs = [(a, b1), (a, b2), (a, b3), (b1, a), (a[:5000], a[200:5300])]
     exp = [oracle.align_linear(x, y, CONFIG_TOML, False) for x, y in pairs]
     blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+    monkeypatch.setenv("GX_TICKETS", "1")        # the band belongs to ticket-mode plans (resident strips keep codes everywhere)
     for band, want_fallback in (("64", True), (None, None), ("0", False)):
         if band is None:
             monkeypatch.delenv("GX_CODE_BAND", raising=False)
@@ -266,6 +267,7 @@ def test_code_band_and_fallback(gx, oracle, monkeypatch):
             assert plan.stat(23) == 1.0
         plan.close()
     monkeypatch.delenv("GX_CODE_BAND", raising=False)
+    monkeypatch.delenv("GX_TICKETS", raising=False)
 
 
 def test_corona_all_vs_all(gx, oracle, goldens):
