@@ -98,7 +98,10 @@ int gx_align_pair(const uint8_t *s1, uint64_t m, const uint8_t *s2, uint64_t n,
 /* ---- many independent pairs in one call (pairs scattered over the SMs of this context's GPU).
  * Pair p is seq_blob[off1[p] .. off1[p]+len1[p]) vs seq_blob[off2[p] .. off2[p]+len2[p]).
  * With GX_FLAG_TRACEBACK pair p's ops go to ops_blob[ops_off[p] ..] and ops_off must have n_pairs+1
- * entries with ops_off[p+1]-ops_off[p] >= len1[p]+len2[p]+1. */
+ * entries with ops_off[p+1]-ops_off[p] >= len1[p]+len2[p]+1.
+ * The one-shot calls (gx_align_pair / gx_align_batch / gx_score_batch / gx_nw_score_banded) keep the plan of their
+ * previous call and reuse it when the next call has the same lengths, scores, mode and flags (a stream of equally
+ * shaped batches pays for plan creation once); another shape replaces it, gx_shutdown releases it. */
 int gx_align_batch(const uint8_t *seq_blob, uint64_t blob_len,
                    const uint64_t *off1, const uint64_t *len1,
                    const uint64_t *off2, const uint64_t *len2, uint64_t n_pairs,
@@ -113,7 +116,10 @@ int gx_score_batch(const uint8_t *seq_blob, uint64_t blob_len,
                    gx_scores sc, int is_local, int64_t *scores);
 
 /* ---- the same, split into phases so that callers can keep inputs resident in HBM, overlap
- * copies, and time the kernels alone.  gx_align_batch == create + upload + execute + fetch + destroy. */
+ * copies, and time the kernels alone.  gx_align_batch == create + upload + execute + fetch (+ destroy, deferred).
+ * gx_plan_execute never returns a wrong result for speed's sake: a resident-strips fill that gives up waiting is
+ * repeated in ticket mode, and a global traceback plan that stores direction codes only near the table's diagonal
+ * (the "code band") is repeated with codes everywhere if any path leaves the band. */
 typedef struct gx_plan gx_plan;
 int gx_plan_create(const uint64_t *len1, const uint64_t *len2, uint64_t n_pairs,
                    gx_scores sc, int is_local, int flags, gx_plan **plan);
@@ -126,7 +132,9 @@ void gx_plan_destroy(gx_plan *plan);
 /* introspection for benchmarks: what==0 fill ms, 1 walk ms, 2 kernels launched by the last execute,
  * 3 cells (sum (m+1)(n+1)), 4 traceback bytes written per execute, 5 device bytes held by the plan,
  * 6 h2d bytes per upload, 7 d2h bytes per fetch, 8 tiles, 9 kernel family (0 wavefront, 1 read batch),
- * 15 K, 17 recurrence form (1 = CHAIN1), 18 ms of the GX_FLAG_LCS_AT_MAX passes */
+ * 15 K, 17 recurrence form (1 = CHAIN1), 18 ms of the GX_FLAG_LCS_AT_MAX passes, 19 R, 20 ticket-mode retries,
+ * 21 resident strips (1) or tickets (0), 22 steps per hand-off batch, 23 share of the cells in code-writing tiles,
+ * 24 executes repeated because a path left the code band */
 double gx_plan_stat(const gx_plan *plan, int what);
 /* debug (GX_FILL_STATS=2): per tile {ticket ns, first DP step ns, end ns, pair<<48|panel<<32|strip<<12|sm}; cap_words >= 4 * tiles */
 int gx_plan_debug_timeline(gx_plan *plan, uint64_t *out, uint64_t cap_words);

@@ -270,6 +270,34 @@ def test_code_band_and_fallback(gx, oracle, monkeypatch):
     monkeypatch.delenv("GX_TICKETS", raising=False)
 
 
+@pytest.mark.parametrize("chain1", [0, 1])
+@pytest.mark.parametrize("k,r", KR_COMBOS)
+def test_code_band_kernel_ragged(gx, oracle, k, r, chain1, monkeypatch):
+    """the two-variant (code band) fill kernel for every register tile and both recurrence forms, on ragged tables whose
+    tiles are partly inside and partly outside a forced 300-column band; similar pairs stay inside it, unrelated ones
+    wander out and take the fallback"""
+    force_kr(monkeypatch, k, r)
+    monkeypatch.setenv("GX_CHAIN1", str(chain1))
+    monkeypatch.setenv("GX_TICKETS", "1")
+    monkeypatch.setenv("GX_CODE_BAND", "300")
+    rng = np.random.default_rng(17)
+    dims = [(4200, 4000), (4097, 5300), (8193, 7000), (2000, 2100), (5000, 4000), (4096, 4096), (700, 9000)]
+    for similar in (True, False):
+        pairs = [random_pair(rng, m, n, similar=similar, sub=0.1, indel=0.01) for m, n in dims]
+        blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
+        plan = gx.Plan(len1, len2, CONFIG_TOML, False, traceback=True)
+        plan.upload(blob, off1, off2)
+        plan.execute()
+        res, ops, ops_off = plan.fetch()
+        if similar:
+            assert plan.stat(23) < 0.9 and plan.stat(24) == 0, (plan.stat(23), plan.stat(24))   # band in use, no fallback
+        for q, (a, b) in enumerate(pairs):
+            o = oracle.align_linear(a, b, CONFIG_TOML, False)
+            assert res["score"][q] == o.score and res["n_ops"][q] == len(o.ops), (k, chain1, similar, q)
+            assert np.array_equal(ops[int(ops_off[q]):int(ops_off[q]) + len(o.ops)], o.ops), (k, chain1, similar, q)
+        plan.close()
+
+
 def test_corona_all_vs_all(gx, oracle, goldens):
     """BASELINE config 3: 45 pairs of ~30 kb genomes, global, score + traceback, one batch."""
     order = goldens["corona_order"]
