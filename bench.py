@@ -481,6 +481,8 @@ def run_plan_workload(env, args, name: str, steps: int, warmup: int, headline: b
             if env.world == 1:
                 roof["traffic"], roof["traffic_source"] = ncu_traffic(name)
             roof["algorithmic_bytes"] = code_bytes * code_frac    # 2-bit codes written once per cell of a code-writing tile
+            roof["traffic_note"] = ("DRAM traffic also holds the strip-boundary hand-off (8 B per row per strip boundary, written once and "
+                                    "polled through L2): ~1.25 GB per step for the 45 pairs at K=8")
             gbs = code_bytes * code_frac / (my_fill * 1e-3) / 1e9
             hbm = {"bound": "hbm", "achieved": gbs, "peak": env.peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / env.peaks["hbm_gbs"],
                    "what": "traceback codes written once per cell (0.25 B/cell)", "peak_source": env.peaks["source"]}
