@@ -129,7 +129,7 @@ static void pool_free(Ctx *c, void *p) {
 // Debug / experiment switches.  The environment is read ONCE per plan (gx_plan_create) or per streamed
 // batch call, never on the execute path; -1 = not set.
 struct Tunables {
-    int r = -1, batch = -1, code_band = -1;
+    int r = -1, batch = -1, code_band = -1, band_resident = 1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
         fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0, test_abort = 0;
 };
@@ -142,6 +142,7 @@ static Tunables read_tunables() {
     t.k = env_int("GX_K", -1);
     t.r = env_int("GX_R", -1);
     t.batch = env_int("GX_BATCH", -1);
+    t.band_resident = env_int("GX_BAND_RESIDENT", 1);   // 0: resident-strips plans keep codes in every tile
     t.code_band = env_int("GX_CODE_BAND", -1);   // 0: codes in every tile; > 0: half-width of the code band in columns
     t.chain1 = env_int("GX_CHAIN1", -1);
     t.tickets = getenv("GX_TICKETS") ? 1 : -1;
@@ -766,11 +767,12 @@ static int plan_create_locked(const uint64_t *len1, const uint64_t *len2, uint64
         A((size_t)n_pairs * 2 * pl->carry_words * 4 + 16, (void **)&pl->d_carry);
     }
     A(n_pairs * sizeof(DevResult), (void **)&pl->d_results);
-    // code band (see gx_common.cuh): global traceback plans in ticket mode.  A global alignment's path runs along the scaled
-    // diagonal j = i*n/m (all 45 coronavirus pairs stay within 316 columns of it): default half-width 1024 + |m - n| columns.
-    // Resident-strips plans keep codes everywhere: their strips run as lone warps, which the two-variant kernel slows down.
+    // code band (see gx_common.cuh): global traceback plans.  A global alignment's path runs along the scaled diagonal
+    // j = i*n/m (all 45 coronavirus pairs stay within 316 columns of it): default half-width 1024 + |m - n| columns.
+    // (6-pair shard, resident strips: fill 4.67 -> 4.07 ms; a single pair gains nothing -- its chain of strips runs at the
+    // pace of the strips that do write codes -- and loses nothing.)
     std::vector<uint8_t> tile_codes;
-    if (pl->traceback && !is_local && !band_col0 && !pl->resident && pl->tun.code_band != 0 && best > 0) {
+    if (pl->traceback && !is_local && !band_col0 && (!pl->resident || pl->tun.band_resident != 0) && pl->tun.code_band != 0 && best > 0) {
         tile_codes.assign(best, 1);
         double with = 0, all = 0;
         for (uint64_t q = 0; q < n_pairs; ++q) {

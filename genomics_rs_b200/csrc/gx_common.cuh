@@ -63,7 +63,7 @@ struct PairDesc {
     const uint32_t *ack;
 };
 
-// Code band (global traceback plans in ticket mode): direction codes are only WRITTEN by tiles within `code_w` columns of
+// Code band (global traceback plans): direction codes are only WRITTEN by tiles within `code_w` columns of
 // the table's scaled diagonal j = i*n/m -- where the path of a global alignment runs; every other tile runs the score-only
 // cell (5 instead of 9 instructions).  One flag byte per tile (FillParams / WalkParams::tile_codes, indexed like tile_best;
 // null = every tile has codes), written by the host, read by the fill (which variant to run) and by the walk, which

@@ -303,9 +303,10 @@ __device__ __forceinline__ void run_batch(int (&eu)[K], int (&du)[K], const int 
     }
 }
 
-// BAND (global traceback plans in ticket mode): the kernel carries BOTH the traceback and the score-only batch variants and
-// picks per tile (FillParams::tile_codes).  A separate instantiation on purpose: a lone warp (resident strips) runs the
-// traceback variant 40 % slower when the second variant is compiled into the same kernel (BRCA2 fill 0.99 -> 1.41 ms).
+// BAND (global traceback plans with a code band): the kernel carries BOTH the traceback and the score-only variant of the
+// tile's batch loops and picks one per tile (FillParams::tile_codes).  The choice is made once per tile, around two complete
+// copies of the loops: dispatching per batch inside shared loops slowed a resident strip's traceback variant by 8-40 %
+// (BRCA2 fill 0.99 -> 1.41 ms) even when the other variant never ran.
 template <int K, int R, bool LOCAL, bool CODES, int TRACK, bool PROF, bool CHAIN1, bool BAND = false>
 __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE_CTAS) gx_fill_kernel(const FillParams P) {
     using G = Geo<K, R>;
@@ -633,62 +634,65 @@ __global__ void __launch_bounds__(CTA_THREADS, CODES ? ctas_per_sm(K) : GX_SCORE
         // phase 0: masked head batches (all batches of a THRU tile), then the unmasked body; phase 1: masked tail.
         // (One copy of each batch variant in the code; nothing here may end up as an out-of-line call -- the DP
         // state lives in registers.)
-        // one batch, in the variant this tile needs: with direction codes, or -- a tile outside the code band of a global
-        // traceback plan -- the score-only cell (both variants live in the kernel; the choice is uniform per tile)
-        auto do_batch = [&](auto masked_c, auto pad_c, uint32_t b, uint2 *outr, uint4 *cdst) __attribute__((always_inline)) {
-            constexpr bool M = decltype(masked_c)::value, PD = decltype(pad_c)::value;
-            if constexpr (BAND) {
-                if (!tcodes) {
-                    run_batch<K, R, LOCAL, false, TRACK, PROF, M, PD, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp, one, s1base, prof4,
-                                                                             inring + (b & 1u) * BR, outr, nullptr, (int)(B * b), rows, lane, kvalid,
-                                                                             c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
-                    return;
+        // The batch loops of one tile, in the variant this tile needs: with direction codes, or -- a tile outside the code
+        // band of a global traceback plan -- the score-only cell.  BAND kernels carry TWO complete copies of the loops and pick
+        // one per tile at this level (dispatching per batch inside shared loops cost a resident strip 8-40 %).
+        auto run_tile = [&](auto codes_c) __attribute__((always_inline)) {
+            constexpr bool WC = decltype(codes_c)::value;
+            uint32_t bt = 0;
+            for (int ph = 0; ph < 2 && !dead; ++ph) {
+                const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
+                for (; bt < m_end && !dead; ++bt) {
+                    uint2 *outr = outring + (bt & 1u) * BR;
+                    uint4 *cdst = WC ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                    GX_CHECK(chk, !WC || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                          pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
+                    if constexpr (!LOCAL && !CODES && TRACK == 0) {
+                        if (thru)
+                            run_batch<K, R, LOCAL, WC, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                            one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                            (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                    }
+                    if (!thru)
+                        run_batch<K, R, LOCAL, WC, TRACK, PROF, true, (TRACK != 0), CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                         one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                         (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                    if (!post(bt, outr)) dead = true;
+                }
+                if (ph != 0 || thru || dead) continue;
+                // Columns right of the table (last strip of a pair) need their keys masked only when a padded cell could
+                // reach the maximum; with s_mismatch < 0 (and g, h+g < 0) every padded cell is strictly smaller than the real
+                // cell it derives from, so the plain body is exact -- the tile reductions ignore winners with j > n.
+                if ((TRACK != 0) && has_pad && P.pad_keys != 0u) {
+                    for (; bt < nb_body && !dead; ++bt) {
+                        uint2 *outr = outring + (bt & 1u) * BR;
+                        uint4 *cdst = WC ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                        GX_CHECK(chk, !WC || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                              pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
+                        run_batch<K, R, LOCAL, WC, TRACK, PROF, false, true, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                  one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                  (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                        if (!post(bt, outr)) dead = true;
+                    }
+                } else {
+                    for (; bt < nb_body && !dead; ++bt) {
+                        uint2 *outr = outring + (bt & 1u) * BR;
+                        uint4 *cdst = WC ? code_base + (size_t)bt * cpb * 32 : nullptr;
+                        GX_CHECK(chk, !WC || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
+                                              pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
+                        run_batch<K, R, LOCAL, WC, TRACK, PROF, false, false, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
+                                                                                   one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
+                                                                                   (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
+                        if (!post(bt, outr)) dead = true;
+                    }
                 }
             }
-            run_batch<K, R, LOCAL, CODES, TRACK, PROF, M, PD, CHAIN1>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp, one, s1base, prof4,
-                                                                     inring + (b & 1u) * BR, outr, cdst, (int)(B * b), rows, lane, kvalid, c1a, cpb,
-                                                                     chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
         };
-        uint32_t bt = 0;
-        for (int ph = 0; ph < 2 && !dead; ++ph) {
-            const uint32_t m_end = (ph == 0 && !thru) ? min(nb_head, nbat) : nbat;
-            for (; bt < m_end && !dead; ++bt) {
-                uint2 *outr = outring + (bt & 1u) * BR;
-                uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
-                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
-                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
-                if constexpr (!LOCAL && !CODES && TRACK == 0) {
-                    if (thru)
-                        run_batch<K, R, LOCAL, CODES, TRACK, PROF, true, false, CHAIN1, true>(eu, du, c2, eo, io, vd, best, best_r, g, hg, ap, bp,
-                                                                                           one, s1base, prof4, inring + (bt & 1u) * BR, outr, cdst,
-                                                                                           (int)(B * bt), rows, lane, kvalid, c1a, cpb, chk, -(int)delta, WARP_SMEM_S1 - (int)delta);
-                }
-                if (!thru) do_batch(std::true_type{}, std::integral_constant<bool, (TRACK != 0)>{}, bt, outr, cdst);
-                if (!post(bt, outr)) dead = true;
-            }
-            if (ph != 0 || thru || dead) continue;
-            // Columns right of the table (last strip of a pair) need their keys masked only when a padded cell could
-            // reach the maximum; with s_mismatch < 0 (and g, h+g < 0) every padded cell is strictly smaller than the real
-            // cell it derives from, so the plain body is exact -- the tile reductions ignore winners with j > n.
-            if ((TRACK != 0) && has_pad && P.pad_keys != 0u) {
-                for (; bt < nb_body && !dead; ++bt) {
-                    uint2 *outr = outring + (bt & 1u) * BR;
-                    uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
-                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
-                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
-                    do_batch(std::false_type{}, std::true_type{}, bt, outr, cdst);
-                    if (!post(bt, outr)) dead = true;
-                }
-            } else {
-                for (; bt < nb_body && !dead; ++bt) {
-                    uint2 *outr = outring + (bt & 1u) * BR;
-                    uint4 *cdst = CODES ? code_base + (size_t)bt * cpb * 32 : nullptr;
-                GX_CHECK(chk, !CODES || ((size_t)(bt + 1) * cpb * 512 <= pd->tile_code_bytes &&
-                                         pd->codes_off + (uint64_t)(p * S + s + 1) * pd->tile_code_bytes <= P.code_bytes), 7);
-                    do_batch(std::false_type{}, std::false_type{}, bt, outr, cdst);
-                    if (!post(bt, outr)) dead = true;
-                }
-            }
+        if constexpr (BAND) {
+            if (tcodes) run_tile(std::true_type{});
+            else run_tile(std::false_type{});
+        } else {
+            run_tile(std::integral_constant<bool, CODES>{});
         }
         flush_pub();
         if (dead) break;

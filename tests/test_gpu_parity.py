@@ -247,8 +247,11 @@ def test_code_band_and_fallback(gx, oracle, monkeypatch):
     pairs = [(a, b1), (a, b2), (a, b3), (b1, a), (a[:5000], a[200:5300])]
     exp = [oracle.align_linear(x, y, CONFIG_TOML, False) for x, y in pairs]
     blob, off1, len1, off2, len2 = gx.pack_pairs(pairs)
-    monkeypatch.setenv("GX_TICKETS", "1")        # the band belongs to ticket-mode plans (resident strips keep codes everywhere)
-    for band, want_fallback in (("64", True), (None, None), ("0", False)):
+    monkeypatch.setenv("GX_TICKETS", "1")
+    for band, want_fallback in (("64", True), (None, None), ("0", False), ("64r", True)):
+        if band == "64r":                       # the same through resident strips (cooperative launch)
+            monkeypatch.delenv("GX_TICKETS", raising=False)
+            band = "64"
         if band is None:
             monkeypatch.delenv("GX_CODE_BAND", raising=False)
         else:
