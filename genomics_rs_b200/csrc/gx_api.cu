@@ -521,24 +521,25 @@ int gx_replay_ops(const uint8_t *ops, uint64_t n_ops, uint64_t start_i, uint64_t
 static void build_ticket_order(const std::vector<uint32_t> &S, const std::vector<uint32_t> &P, const std::vector<uint64_t> &sbase,
                                std::vector<TileDesc> &tiles) {
     const size_t n_pairs = S.size();
+    constexpr uint64_t TS = PANEL_H / 64;   // strips a panel step is worth in the key (64 for 4096-row panels)
     uint64_t vmax = 0;
     std::vector<uint32_t> live;   // pairs that still have tiles at or after v: the sweep costs O(tiles + live pairs x v)
     for (size_t q = 0; q < n_pairs; ++q)
         if (S[q] && P[q]) {
-            vmax = std::max<uint64_t>(vmax, (uint64_t)(P[q] - 1) * 64 + sbase[q] + S[q] - 1);
+            vmax = std::max<uint64_t>(vmax, (uint64_t)(P[q] - 1) * TS + sbase[q] + S[q] - 1);
             live.push_back((uint32_t)q);
         }
     for (uint64_t v = 0; v <= vmax && !live.empty(); ++v) {
         size_t keep = 0;
         for (size_t li = 0; li < live.size(); ++li) {
             const uint32_t q = live[li];
-            const uint64_t last = (uint64_t)(P[q] - 1) * 64 + sbase[q] + S[q] - 1;
+            const uint64_t last = (uint64_t)(P[q] - 1) * TS + sbase[q] + S[q] - 1;
             if (v <= last) live[keep++] = q;
             if (v < sbase[q]) continue;
             const uint64_t sv = v - sbase[q];
-            const uint64_t p_hi = std::min<uint64_t>(P[q] - 1, sv / 64);
-            const uint64_t p_lo = (sv >= S[q]) ? (sv - S[q] + 1 + 63) / 64 : 0;
-            for (uint64_t p2 = p_lo; p2 <= p_hi; ++p2) tiles.push_back({q, (uint32_t)p2, (uint32_t)(sv - 64 * p2), 0});
+            const uint64_t p_hi = std::min<uint64_t>(P[q] - 1, sv / TS);
+            const uint64_t p_lo = (sv >= S[q]) ? (sv - S[q] + 1 + TS - 1) / TS : 0;
+            for (uint64_t p2 = p_lo; p2 <= p_hi; ++p2) tiles.push_back({q, (uint32_t)p2, (uint32_t)(sv - TS * p2), 0});
         }
         live.resize(keep);
     }

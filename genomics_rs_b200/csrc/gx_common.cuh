@@ -9,7 +9,10 @@ namespace gx {
 constexpr int NEG32 = -(1 << 30);
 
 // Rows of one panel: a tile is (panel p, strip s) = PANEL_H rows x 32*K columns, owned by one warp.
-constexpr int PANEL_H_LOG2 = 12;
+#ifndef GX_PANEL_LOG2
+#define GX_PANEL_LOG2 12
+#endif
+constexpr int PANEL_H_LOG2 = GX_PANEL_LOG2;
 constexpr int PANEL_H = 1 << PANEL_H_LOG2;
 // The fill kernel has no CTA-level cooperation (per-warp shared memory, no __syncthreads), so the same code runs as
 // 8-warp CTAs (2 per SM) or as single-warp CTAs (16 per SM).  Single-warp CTAs let the block scheduler spread a small
