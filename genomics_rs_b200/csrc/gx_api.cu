@@ -131,7 +131,7 @@ static void pool_free(Ctx *c, void *p) {
 struct Tunables {
     int r = -1, batch = -1, code_band = -1, band_resident = 1;
     int k = -1, chain1 = -1, tickets = -1, resident = -1, wpc = -1, grid_cap = -1, pad_keys = 0, poll_nap = 0, start_lead = 0,
-        fill_stats = 0, walk_stats = 0, no_stream = 0, reads32 = 0, test_abort = 0;
+        fill_stats = 0, walk_stats = 0, walk_rows = 0, no_stream = 0, reads32 = 0, test_abort = 0;
 };
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
@@ -154,6 +154,7 @@ static Tunables read_tunables() {
     t.start_lead = env_int("GX_START_LEAD", 0);
     t.fill_stats = env_int("GX_FILL_STATS", 0);
     t.walk_stats = getenv("GX_WALK_STATS") ? 1 : 0;
+    t.walk_rows = env_int("GX_WALK_ROWS", 0);          // 256 / 512: rows of a code window of the walk
     t.no_stream = getenv("GX_NO_STREAM") ? 1 : 0;
     t.reads32 = getenv("GX_READS32") ? 1 : 0;
     t.test_abort = getenv("GX_TEST_ABORT") ? 1 : 0;
@@ -328,24 +329,25 @@ static int launch_fill(gx_plan *pl, const FillParams &fp, int grid_cap, int trac
 }
 
 typedef void (*WalkKernel)(const WalkParams);
-static int launch_walk(gx_plan *pl, const WalkParams &wp) {
+static int launch_walk(gx_plan *pl, WalkParams wp) {
     WalkKernel kern = nullptr;
-    uint32_t smem_max = 0;
-#define GX_WALK(k, r)                           \
-    if (pl->K == k && pl->R == r) {             \
-        kern = gx_walk_kernel<k, r>;            \
-        smem_max = walk_smem_bytes(k, r);       \
-    }
+#define GX_WALK(k, r) \
+    if (pl->K == k && pl->R == r) kern = gx_walk_kernel<k, r>;
     GX_COMBOS(GX_WALK)
 #undef GX_WALK
     if (!kern) {
         g_err = "no walk kernel for this (K, R)";
         return GX_ERR_INTERNAL;
     }
-    const uint32_t smem = wp.traceback ? smem_max : 0u;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    // one CTA per pair: path warp + emit warp with traceback, a single warp (start cell and score only) without
-    kern<<<(unsigned)pl->n_pairs, wp.traceback ? 64 : 32, smem, pl->ctx->stream>>>(wp);
+    // rows of a code window: 512 lets a diagonal path cross a whole strip (32*K <= 256 columns for K <= 8) inside one window;
+    // 256 keeps more walk CTAs resident per SM when there are many pairs (three window buffers per CTA)
+    uint32_t rows = (pl->K <= 8 && pl->n_pairs <= 2u * (uint32_t)pl->ctx->sm_count) ? 512u : 256u;
+    if (pl->tun.walk_rows == 256 || pl->tun.walk_rows == 512) rows = (uint32_t)pl->tun.walk_rows;
+    wp.win_rows = rows;
+    const uint32_t smem = wp.traceback ? walk_smem_bytes(pl->K, pl->R, rows) : 0u;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(pl->K, pl->R, 512u)));
+    // one CTA per pair: path warp, loader warp and two emit warps with traceback; a single warp (start cell and score only) without
+    kern<<<(unsigned)pl->n_pairs, wp.traceback ? WALK_THREADS : 32, smem, pl->ctx->stream>>>(wp);
     CK(cudaGetLastError());
     return GX_OK;
 }

@@ -136,6 +136,7 @@ struct WalkParams {
     const uint8_t *tile_codes;       // code band: one flag per tile, or null (every tile has codes)
     uint32_t *check;                 // checked build: where a failed bounds check records its site (control block word 2)
     uint64_t code_bytes, ops_bytes;  // sizes of the codes / ops buffers (checked build)
+    uint32_t win_rows;               // rows of a code window of the walk (256 or 512)
 };
 
 // ---------------------------------------------------------------------------------------------

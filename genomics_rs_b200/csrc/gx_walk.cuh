@@ -7,26 +7,42 @@
 //               off-by-one match label is_match(i,j) (algo.rs:354, sequence.rs:102-115),
 //               open/extend labels from last_choice (algo.rs:373-379,388-394),
 //               checked_sub index update (algo.rs:412-417), stop at (0,0) (algo.rs:419-421).
-// One warp per pair, two levels of parallelism inside the inherently sequential walk:
-// (a) a 256-row window of code chunks spanning the whole strip is fetched into shared memory with one round
-//     of asynchronous 16-byte copies (cp.async) -- one HBM latency per window instead of one per code line;
-// (b) run following: the path consists of runs of equal codes, so lane x inspects the cell x moves ahead in
-//     the current direction, a ballot finds the run length, and up to 32 ops (labels, counters, coalesced
-//     byte stores) are emitted per iteration.
+// One CTA of four warps per pair.  The walk is m+n dependent steps; what it costs is the length of the dependent
+// chain ONE warp has to issue per run of equal codes, so everything that is not path finding lives in other warps:
+//   path warp   (warp 0)    follows the stored direction codes inside a window of code chunks held in shared memory:
+//                           lane x inspects the cell x moves ahead in the current direction, a ballot gives the run
+//                           length, the look-ahead lane that already read the turn cell supplies the next direction.
+//                           One self-contained 16-byte descriptor per run goes into a shared-memory ring.
+//   loader warp (warp 2)    owns the code windows: on request it copies the chunks of (tile, row range) into one of three
+//                           window buffers (cp.async, 16 B each) and checks the tile's code-band flag.  The path warp asks
+//                           for the windows it will probably need next (left neighbour strip at the rows where a
+//                           diagonal path leaves this one; the rows above) when it enters a window, so a window change
+//                           normally costs a few shared-memory reads.
+//   emit warps  (warps 1,3) pop descriptors (even / odd sequence numbers) and do the rest: the off-by-one match labels
+//                           is_match(i, j) (characters from global memory / L1), open/extend labels, the four counters,
+//                           the coalesced op stores, the end cell.
 #pragma once
 #include "gx_common.cuh"
 #include "gx_fill.cuh"
 
 namespace gx {
 
-// dynamic shared memory of one walk CTA: a 1 KB control block (descriptor ring between the two warps, tail word,
-// debug counters) and two code-window buffers.
-// A window is 256 rows of one strip = 256/R (+1) row blocks + 31 steps of lane skew, 64/(R*K) steps per code chunk.
-__host__ __device__ constexpr uint32_t walk_chunks(int K, int R) { return (uint32_t)((256 / R + 1 + 31 + 64 / (R * K) - 1) / (64 / (R * K)) + 1); }
-__host__ __device__ constexpr uint32_t walk_buf_bytes(int K, int R) { return walk_chunks(K, R) * 32 * 16; }
-constexpr uint32_t WALK_CTRL_BYTES = 1024;
-constexpr uint32_t WALK_RING = 32;          // run descriptors in flight between the path warp and the emit warp
-__host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R) { return WALK_CTRL_BYTES + 2 * walk_buf_bytes(K, R); }
+// dynamic shared memory of one walk CTA: a 2 KB control block (descriptor ring, request ring, tails, ready words, partial
+// results, debug counters) and three code-window buffers.
+// A window is `rows` rows of one strip = rows/R (+1) row blocks + 31 steps of lane skew, 64/(R*K) steps per code chunk.
+__host__ __device__ constexpr uint32_t walk_chunks(int K, int R, uint32_t rows) {
+    return (uint32_t)((rows / R + 1 + 31 + 64 / (R * K) - 1) / (64 / (R * K)) + 1);
+}
+__host__ __device__ constexpr uint32_t walk_buf_bytes(int K, int R, uint32_t rows) { return walk_chunks(K, R, rows) * 32 * 16; }
+constexpr uint32_t WALK_CTRL_BYTES = 2048;
+constexpr uint32_t WALK_RING = 64;          // run descriptors in flight between the path warp and the emit warps
+constexpr uint32_t WALK_REQ = 8;            // window requests in flight between the path warp and the loader warp (<= 3 used)
+constexpr uint32_t WALK_NBUF = 3;           // window buffers: the current one and two prefetch targets
+constexpr uint32_t WALK_THREADS = 128;
+__host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R, uint32_t rows) {
+    return WALK_CTRL_BYTES + WALK_NBUF * walk_buf_bytes(K, R, rows);
+}
+static_assert(PANEL_H_LOG2 <= 12, "window requests carry panel rows in 12 bits");
 
 __device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *p) {
     uint32_t v;
@@ -44,18 +60,15 @@ __device__ __forceinline__ uint4 lds_volatile_uint4(const uint4 *p) {
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+// a code word of the current window (written by the loader warp's cp.async: never cached in a register across a window change)
+__device__ __forceinline__ uint32_t lds_code_word(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 
-// One CTA of TWO warps per pair (one warp when no traceback is wanted).  The walk is m+n dependent steps, so what it costs
-// is the instructions ONE warp has to issue per step of the dependent chain (a lone warp issues ~0.4 instructions per
-// clock).  The chain is therefore kept to the path finding alone:
-//   path warp (warp 0)  follows the stored direction codes: code windows in shared memory (cp.async, double-buffered,
-//                       next window prefetched), run following (lane x inspects the cell x moves ahead, a ballot gives
-//                       the run length), and pushes one descriptor (i, j, direction, run length) per run into a ring;
-//   emit warp (warp 1)  pops descriptors and does everything that is not on the chain: the off-by-one match labels
-//                       is_match(i, j) (characters straight from global memory / L1), open/extend labels, the four
-//                       counters, the coalesced op stores, the end cell.
 template <int K, int R>
-__global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams P) {
     const uint32_t q = blockIdx.x;
     if (q >= P.n_pairs) return;
     const int lane = threadIdx.x & 31;
@@ -133,253 +146,381 @@ __global__ void __launch_bounds__(64) gx_walk_kernel(const WalkParams P) {
         if (threadIdx.x == 0) P.results[q] = res;
         return;
     }
+    if (i == 0 && j == 0) {
+        // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
+        if (threadIdx.x == 0) {
+            P.ops[pd->ops_off] = 0;
+            res.n_ops = 1;
+            res.matches = 1;
+            P.results[q] = res;
+        }
+        return;
+    }
+
     using G = Geo<K, R>;
-    constexpr int SPC = G::SPC;
-    constexpr int WR = 256;                               // rows per window; the window spans the whole strip width
-    constexpr int NCH = (int)walk_chunks(K, R);           // code chunks per fill-lane in a window
+    constexpr uint32_t SPC = G::SPC;
+    const uint32_t WR = P.win_rows;                          // rows per window (256 or 512); a window spans the strip's width
+    const uint32_t BUF_BYTES = walk_buf_bytes(K, R, WR);
     extern __shared__ __align__(16) uint8_t walk_smem[];
-    // descriptor ring, LL style: {i, j, code | run << 8, sequence number}.  One lane writes a descriptor with ONE 16-byte
-    // shared-memory store and the emit warp polls the slot until it carries the sequence number it expects: no head word,
-    // no fence on the path warp's dependent chain.  `tail` (descriptors consumed) is only read when the ring looks full.
+    // descriptor ring, LL style: {i | tag, j, direction | previous direction << 2 | run << 4 | tag, ops emitted before}.  The path warp
+    // writes a descriptor with ONE 16-byte shared-memory store and the emit warp it belongs to (sequence number parity) polls
+    // the slot until it carries the lap tag it expects: no head word, no fence on the path warp's dependent chain.
+    // tail[e] (descriptors emit warp e is done with) is only read when the ring looks full.
     uint4 *ring = reinterpret_cast<uint4 *>(walk_smem);
-    uint32_t *tail = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16);
-    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(walk_smem + WALK_RING * 16 + 16);
+    uint4 *req = reinterpret_cast<uint4 *>(walk_smem + WALK_RING * 16);              // {panel, strip, r0 | r1 << 12 | buffer << 24 | quit << 31, seq}
+    uint32_t *tail = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16 + WALK_REQ * 16);
+    uint32_t *ready = tail + 4;                                                        // per buffer: last request finished | no-codes << 31
+    uint32_t *part = tail + 8;                                                         // per emit warp: 8 words of partial results
+    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(tail + 24);
     uint8_t *bufs = walk_smem + WALK_CTRL_BYTES;
-    if (threadIdx.x < WALK_RING) ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);     // sequence numbers start at 1
-    if (threadIdx.x == 0) sts_volatile_u32(tail, 0u);
+    if (threadIdx.x < WALK_RING) ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);       // lap tags start at 1
+    if (threadIdx.x < WALK_REQ) req[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);         // request numbers start at 1
+    if (threadIdx.x < 32) tail[threadIdx.x] = 0u;                                       // tails, ready words, partial results
     __syncthreads();
 
     if (wid == 0) {
         // ================================================================ path warp
-        // Two window buffers: the walk reads buffer `cb`; the other one receives the window the walk will probably need
-        // next (prefetched with cp.async while the walk runs).  Per buffer: code chunks [chunk][fill-lane].
-        constexpr uint32_t BUF_BYTES = walk_buf_bytes(K, R);
-        uint32_t cb = 0;
-        const uint4 *win = reinterpret_cast<const uint4 *>(bufs);
-        // prefetched window (in buffer cb ^ 1): tile (np, ns), local rows [nr0, nr1]; np = 0xffffffff: none
-        uint32_t np = 0xffffffffu, ns = 0, nr0 = 0, nr1 = 0;
-        // current window: tile (wp, ws), local rows [wr0, wr1], first chunk wc0
-        uint32_t wp = 0xffffffffu, ws = 0, wr0 = 0, wr1 = 0, wc0 = 0;
-        uint32_t pushed = 0, tail_seen = 0;
-        auto push = [&](uint32_t pi, uint32_t pj, uint32_t meta) __attribute__((always_inline)) {
-            if (pushed - tail_seen >= WALK_RING) {           // looks full: refresh the consumer's count (rare: the emit warp is faster)
-                do {
-                    tail_seen = lds_volatile_u32(tail);
-                } while (pushed - tail_seen >= WALK_RING);
+        // lane `lane` looks y = 31 - lane moves ahead: the run length is then a count of leading ones of the ballot.
+        // y and the ring's shared-memory address make a round trip through shared memory: values ptxas cannot re-derive
+        // from %tid / the CTA's shared window inside the loop (it otherwise does, with 20-clock S2R / S2UR reads per run).
+        uint32_t y, ring_s;
+        {
+            uint32_t *scratch = tail + 32;
+            sts_volatile_u32(scratch + lane, 31u - (uint32_t)lane);
+            sts_volatile_u32(scratch + 32 + lane, smem_u32(ring));
+            y = lds_volatile_u32(scratch + lane);
+            ring_s = lds_volatile_u32(scratch + 32 + lane);
+        }
+        uint32_t pushed = 0, safe = WALK_RING;               // descriptors pushed; pushes below `safe` find their slot free
+        uint32_t nops = 0, prevc = 0;                        // ops pushed so far; direction of the previous run (Match, algo.rs:338)
+        uint32_t dbg_ringwait = 0;
+        auto push = [&](uint32_t pi, uint32_t pj, uint32_t meta, uint32_t before) __attribute__((always_inline)) {
+            if (pushed >= safe) {           // slot reuse: its previous descriptor (RING back) must have been consumed
+                dbg_ringwait++;
+                do {                        // tail[e] = 1 + the last descriptor emit warp e is done with: everything below both is consumed
+                    safe = min(lds_volatile_u32(tail), lds_volatile_u32(tail + 1)) + WALK_RING;
+                } while (pushed >= safe);
             }
+            // the lap tag rides in both 8-byte halves: a reader that caught the halves from different laps -- should
+            // 16-byte shared accesses ever be split -- does not accept the slot.  Every lane stores the same value (no branch).
+            const uint32_t tag = ((pushed / WALK_RING + 1u) & 7u) << 29;
+            asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ring_s + (pushed % WALK_RING) * 16u), "r"(pi | tag), "r"(pj),
+                         "r"(meta | tag), "r"(before)
+                         : "memory");
             pushed++;
-            // (the lap number rides in the top bits of the first half as well: a reader that caught the two 8-byte halves of the
-            // slot from different laps -- should 16-byte shared accesses ever be split -- does not accept it)
-            if (lane == 0) sts_volatile_uint4(ring + (pushed - 1u) % WALK_RING, make_uint4(pi | (((pushed >> 5) & 7u) << 29), pj, meta, pushed));
         };
 
-        // code of cell (ci, cj): 0 S / 1 I / 2 D / 3 stop; 7 = not in the current window (a run must end before it)
-        // Straight-line (no branches): the lookup is on the loop-carried chain of the walk.
-        const uint32_t bnd_row0 = local ? 3u : 1u, bnd_col0 = local ? 3u : 2u;
-        auto cell_code = [&](uint32_t ci, uint32_t cj) __attribute__((always_inline)) -> uint32_t {
-            const uint32_t jj = cj - 1u, ii = ci - 1u;            // wrap to 0xffffffff on the boundaries: never "in window"
-            const uint32_t l = (jj % G::W) / K, k = jj % K;
-            const uint32_t r = ii & (PANEL_H - 1);
-            const bool inwin = ((ii >> PANEL_H_LOG2) == wp) & ((jj / G::W) == ws) & ((r - wr0) <= (wr1 - wr0));
-            const uint32_t t = r / R + l;                         // the step at which fill-lane l worked on this row's block
-            const uint32_t bitpos = (((t % SPC) * R + r % R) * K + k) * 2;
-            const uint32_t widx = inwin ? (((t / SPC - wc0) * 32 + l) * 4 + (bitpos >> 5)) : 0u;
-            GX_CHECK(P.check, widx < walk_buf_bytes(K, R) / 4, 21);
-            const uint32_t word = reinterpret_cast<const uint32_t *>(win)[widx];
-            uint32_t code = inwin ? ((word >> (bitpos & 31u)) & 3u) : 7u;
-            code = (cj == 0u) ? bnd_col0 : code;                  // column 0: only delete_score is finite; local stops
-            code = (ci == 0u) ? ((cj == 0u) ? 0u : bnd_row0) : code;   // row 0; origin: sub_score == max == 0 (algo.rs:195-202)
-            return code;
+        // ---- window state
+        uint32_t cbase = 0;                 // shared-memory address of the current window buffer
+        int rrel = 0, jw = 0, woff = 0;     // row relative to the buffer's first chunk, column in the strip, first window row (same base)
+        uint32_t cb = 0;                    // current buffer
+        // what each buffer holds / will hold: tile (bp, bs), panel rows [br0, br1], the request that fills it
+        uint32_t bp[WALK_NBUF], bs[WALK_NBUF], br0[WALK_NBUF], br1[WALK_NBUF], bq[WALK_NBUF];
+#pragma unroll
+        for (uint32_t b = 0; b < WALK_NBUF; ++b) {
+            bp[b] = 0xffffffffu;
+            bs[b] = br0[b] = br1[b] = bq[b] = 0u;
+        }
+        uint32_t nreq = 0;
+        auto post = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) -> uint32_t {
+            nreq++;
+            sts_volatile_uint4(req + nreq % WALK_REQ, make_uint4(p, s_, r0 | (r1 << 12) | (b << 24), nreq));
+            return nreq;
+        };
+        // code of the window cell (row rr relative to the buffer's first chunk, column jc of the strip): 0 S / 1 I / 2 D / 3 stop
+        auto code_at = [&](uint32_t rr, uint32_t jc) __attribute__((always_inline)) -> uint32_t {
+            const uint32_t l = jc / K, t = rr / R + l;            // the step at which fill-lane l worked on this row's block
+            const uint32_t idx2 = ((t / SPC) * 32u + l) * 64u + ((t % SPC) * R + rr % R) * K + jc % K;
+            GX_CHECK(P.check, (idx2 >> 4) * 4u < BUF_BYTES, 21);
+            const uint32_t word = lds_code_word(cbase + (idx2 >> 4) * 4u);
+            return (word >> ((idx2 & 15u) * 2u)) & 3u;
         };
 
-        unsigned long long dbg_iters = 0, dbg_reloads = 0;
+        uint32_t dbg_reloads = 0, dbg_miss = 0;
         long long dbg_reload_cyc = 0;
         bool left_band = false;
         const long long dbg_t0 = clock64();
-        if (!(i == 0 && j == 0)) {
-            uint32_t c0 = cell_code(i, j);
+        bool walking = (i != 0 && j != 0);
+        while (walking) {
+            // ---------------- (i, j) is an interior cell outside the current window: change windows
+            dbg_reloads++;
+            const long long dbg_r0 = P.debug ? clock64() : 0;
+            const uint32_t jj = j - 1u, ii = i - 1u;
+            const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
+            uint32_t hit = WALK_NBUF;
+#pragma unroll
+            for (uint32_t b = 0; b < WALK_NBUF; ++b)
+                if (b != cb && bp[b] == tp && bs[b] == ts && tr >= br0[b] && tr <= br1[b]) hit = b;
+            if (hit == WALK_NBUF) {
+                // neither prediction holds this cell: load the window that ends at this row into the buffer just left
+                dbg_miss++;
+                hit = cb;
+                const uint32_t r0 = (tr >= WR - 1u) ? tr - (WR - 1u) : 0u;
+                const uint32_t sq = post(hit, tp, ts, r0, tr);
+#pragma unroll
+                for (uint32_t b = 0; b < WALK_NBUF; ++b)
+                    if (b == hit) {
+                        bp[b] = tp;
+                        bs[b] = ts;
+                        br0[b] = r0;
+                        br1[b] = tr;
+                        bq[b] = sq;
+                    }
+            }
+            cb = hit;
+            uint32_t wr0 = 0, wr1 = 0, wq = 0;
+#pragma unroll
+            for (uint32_t b = 0; b < WALK_NBUF; ++b)
+                if (b == cb) {
+                    wr0 = br0[b];
+                    wr1 = br1[b];
+                    wq = bq[b];
+                }
+            uint32_t st;
+            do {
+                st = lds_volatile_u32(ready + cb);
+            } while ((st & 0x7fffffffu) != wq);
+            __threadfence_block();                                // the loader's copies are visible before the first code read
+            // code band: a tile away from the table's diagonal holds no codes.  The path has left the band: give
+            // up -- the host repeats the execute with codes everywhere (exactness never depends on the band).
+            if (st >> 31) {
+                left_band = true;
+                break;
+            }
+            const uint32_t wc0 = (wr0 / R) / SPC;
+            cbase = smem_u32(bufs + cb * BUF_BYTES);
+            rrel = (int)(tr - wc0 * SPC * R);
+            woff = (int)(wr0 - wc0 * SPC * R);
+            jw = (int)(jj % G::W);
+            asm volatile("" : "+r"(rrel), "+r"(woff), "+r"(jw), "+r"(cbase));   // loop-carried registers, not expressions to re-derive per run
+            uint32_t c0 = code_at((uint32_t)rrel, (uint32_t)jw);
+            // ask for the windows the walk will probably need next, into the two other buffers.  A diagonal path leaves this
+            // window on the left after jw + 1 rows: the left neighbour strip around that row, with WR/4 rows of slack below it
+            // (insertions) and the rest above (deletions, and the way across that strip); and the rows above this window.
+            {
+                uint32_t o1 = (cb + 1u) % WALK_NBUF, o2 = (cb + 2u) % WALK_NBUF;
+                const int pred = (int)tr - (int)(jw + 1);
+                const bool want_left = ts > 0 && pred + (int)(WR / 4u) >= 0;
+                const bool want_top = wr0 > 0 || tp > 0;
+                uint32_t lp = 0xffffffffu, ls = 0, lr0 = 0, lr1 = 0, lq = 0;
+                uint32_t up = 0xffffffffu, us = 0, ur0 = 0, ur1 = 0, uq = 0;
+                if (want_left) {
+                    lp = tp;
+                    ls = ts - 1u;
+                    lr1 = (uint32_t)min((int)tr, pred + (int)(WR / 4u));
+                    lr0 = (lr1 >= WR - 1u) ? lr1 - (WR - 1u) : 0u;
+                    lq = post(o1, lp, ls, lr0, lr1);
+                }
+                if (want_top) {
+                    us = ts;
+                    if (wr0 > 0) {
+                        up = tp;
+                        ur1 = wr0 - 1u;
+                        ur0 = (ur1 >= WR - 1u) ? ur1 - (WR - 1u) : 0u;
+                    } else {
+                        up = tp - 1u;
+                        ur1 = PANEL_H - 1;
+                        ur0 = PANEL_H - WR;
+                    }
+                    uq = post(o2, up, us, ur0, ur1);
+                }
+#pragma unroll
+                for (uint32_t b = 0; b < WALK_NBUF; ++b) {
+                    if (b == o1) {
+                        bp[b] = lp;
+                        bs[b] = ls;
+                        br0[b] = lr0;
+                        br1[b] = lr1;
+                        bq[b] = lq;
+                    }
+                    if (b == o2) {
+                        bp[b] = up;
+                        bs[b] = us;
+                        br0[b] = ur0;
+                        br1[b] = ur1;
+                        bq[b] = uq;
+                    }
+                }
+            }
+            if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;
+            if (c0 == 3u) break;                          // local alignment ends here; the cell is not emitted (algo.rs:401-405)
+
+            // ---------------- run following inside the window
             for (;;) {
-                dbg_iters++;
-                if (c0 == 7u) {
-                    dbg_reloads++;
-                    const long long dbg_r0 = P.debug ? clock64() : 0;
-                    const uint32_t jj = j - 1, ii = i - 1;
-                    const uint32_t tp = ii >> PANEL_H_LOG2, ts = jj / G::W, tr = ii & (PANEL_H - 1);
-                    // code band: a tile away from the table's diagonal holds no codes.  The path has left the band: give
-                    // up -- the host repeats the execute with codes everywhere (exactness never depends on the band).
-                    if (P.tile_codes && P.tile_codes[pd->tile_base + tp * pd->S + ts] == 0) {
-                        left_band = true;
+                // lane y looks y moves ahead in the direction of c0, as far as the window reaches; the run ends at the
+                // first different code.  Window cells are interior cells (i, j >= 1): no boundary cases on this chain.
+                const bool mi = (c0 != 1u), mj = (c0 != 2u);
+                const uint32_t a = mi ? (uint32_t)(rrel - woff) : 31u, bcol = mj ? (uint32_t)jw : 31u;
+                const uint32_t lim = min(a, bcol);
+                const uint32_t ys = __vimin3_u32(y, a, bcol);
+                const uint32_t cx = code_at((uint32_t)rrel - (mi ? ys : 0u), (uint32_t)jw - (mj ? ys : 0u));
+                const uint32_t same = __ballot_sync(0xffffffffu, (cx == c0) & (ys == y));
+                // >= 1: lane 31 looks at the current cell; <= 31: when every look-ahead agrees the last one still supplies c_next
+                const uint32_t run = (uint32_t)__clz((int)(~same | 1u));
+                // the cell the walk reaches next is the one the lane with y == run just looked at, if the window reached that far
+                const uint32_t c_next = __shfl_sync(0xffffffffu, cx, (int)((31u - run) & 31u));
+                push(i, j, c0 | (prevc << 2) | (run << 4), nops);     // labels, counters and op stores happen in the emit warps
+                prevc = c0;
+                nops += run;
+                // the checked_sub move (algo.rs:412-417): run cells are interior, so neither index underflows
+                i -= mi ? run : 0u;
+                j -= mj ? run : 0u;
+                rrel -= mi ? (int)run : 0;
+                jw -= mj ? (int)run : 0;
+                if (__builtin_expect(run <= lim, 1)) {
+                    c0 = c_next;
+                } else {
+                    // the run ran into the window's edge: the next cell is a boundary cell (row or
+                    // column 0), still inside the window (look it up), or in another window
+                    if (i == 0u || j == 0u) {
+                        walking = false;
                         break;
                     }
-                    // copies of `nch` chunks of tile (p, s) starting at chunk c0w into buffer b (asynchronous)
-                    auto issue_codes = [&](uint32_t b, uint32_t p, uint32_t s_, uint32_t r0, uint32_t r1) __attribute__((always_inline)) {
-                        const uint32_t c0w = (r0 / R) / SPC;
-                        const uint32_t nch = (r1 / R + 31) / SPC - c0w + 1;   // <= NCH
-                        GX_CHECK(P.check, nch <= (uint32_t)NCH && (uint64_t)(c0w + nch) * 512 <= pd->tile_code_bytes &&
-                                              pd->codes_off + (uint64_t)(p * pd->S + s_ + 1) * pd->tile_code_bytes <= P.code_bytes, 23);
-                        const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off +
-                                                                             (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
-                                            (size_t)c0w * 32 + lane;
-                        uint32_t dst = smem_u32(bufs + b * BUF_BYTES) + (uint32_t)lane * 16u;
-                        for (uint32_t q2 = 0; q2 < nch; ++q2) {
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)q2 * 32) : "memory");
-                            dst += 32 * 16;
-                        }
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                    };
-                    __syncwarp();
-                    const bool hit = (np == tp) && (ns == ts) && (tr >= nr0) && (tr <= nr1);
-                    if (hit) {
-                        cb ^= 1u;               // the prefetched window becomes the current one
-                        wp = np;
-                        ws = ns;
-                        wr0 = nr0;
-                        wr1 = nr1;
-                    } else {
-                        // drain whatever is still landing in the other buffer, then load the window that ends at this row:
-                        // rows [r-255, r] x all 32 fill-lanes of the tile
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        wp = tp;
-                        ws = ts;
-                        wr1 = tr;
-                        wr0 = (wr1 >= WR - 1) ? wr1 - (WR - 1) : 0;
-                        issue_codes(cb, wp, ws, wr0, wr1);
-                    }
-                    np = 0xffffffffu;
-                    wc0 = (wr0 / R) / SPC;
-                    win = reinterpret_cast<const uint4 *>(bufs + cb * BUF_BYTES);
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncwarp();
-                    c0 = cell_code(i, j);
-                    // predict the next window and start fetching it into the other buffer: a diagonal path leaves this window
-                    // on the left after (columns to the strip's left edge) rows, at the top after (rows above the entry) rows
-                    {
-                        const uint32_t cin = jj % G::W + 1u, rows_up = tr - wr0 + 1u;
-                        const bool left_ok = ws > 0, top_ok = (wr0 > 0) || (wp > 0);
-                        const bool go_left = left_ok && (cin <= rows_up || !top_ok);
-                        if (go_left) {
-                            np = wp;
-                            ns = ws - 1u;
-                            nr0 = wr0;
-                            nr1 = wr1;
-                        } else if (top_ok) {
-                            ns = ws;
-                            if (wr0 > 0) {
-                                np = wp;
-                                nr1 = wr0 - 1u;
-                                nr0 = (nr1 >= WR - 1) ? nr1 - (WR - 1) : 0;
-                            } else {
-                                np = wp - 1u;
-                                nr1 = PANEL_H - 1;
-                                nr0 = PANEL_H - WR;
-                            }
-                        }
-                        if (np != 0xffffffffu && P.tile_codes && P.tile_codes[pd->tile_base + np * pd->S + ns] == 0)
-                            np = 0xffffffffu;   // nothing to prefetch there
-                        if (np != 0xffffffffu) issue_codes(cb ^ 1u, np, ns, nr0, nr1);
-                    }
-                    if (P.debug) dbg_reload_cyc += clock64() - dbg_r0;
+                    if (rrel < woff || jw < 0) break;
+                    c0 = code_at((uint32_t)rrel, (uint32_t)jw);
                 }
-                if (c0 == 3u) break;                      // local alignment ends on a boundary cell (algo.rs:401-405)
-                // every lane looks x steps ahead in the direction of c0; the run ends at the first different code
-                const uint32_t x = (uint32_t)lane;
-                const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
-                const bool reach = (x * di <= i) & (x * dj <= j);
-                const uint32_t ci = i - (reach ? x * di : 0u), cj = j - (reach ? x * dj : 0u);
-                uint32_t cx = cell_code(ci, cj);
-                cx = (!reach || (x > 0 && ci == 0 && cj == 0)) ? 7u : cx;   // (0,0) is never emitted after a move (algo.rs:419-421)
-                const uint32_t same = __ballot_sync(0xffffffffu, cx == c0);
-                const uint32_t run = (same == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~same) - 1);   // >= 1
-                // the cell the walk reaches next is the one lane `run` just looked at: its code starts the next iteration
-                const uint32_t c_next = __shfl_sync(0xffffffffu, cx, (int)(run & 31u));
-                push(i, j, c0 | (run << 8));              // labels, counters and op stores happen in the emit warp
-                // the checked_sub move (algo.rs:412-417); run cells are all inside the table
-                const bool i_none = di && (i < run), j_none = dj && (j < run);
-                if (i_none && j_none) break;
-                i = i_none ? 0u : i - run * di;
-                j = j_none ? 0u : j - run * dj;
-                if (i == 0 && j == 0) break;
-                // lane `run` looked at exactly (i, j) unless the run used all 32 lanes, the move was clamped, or that
-                // cell was outside the window (7): then look it up (and reload the window at the top of the loop).
-                // A warp-uniform branch: instructions issued are what an iteration costs.
-                if (run < 32u && !i_none && !j_none && c_next != 7u) c0 = c_next;
-                else c0 = cell_code(i, j);
+                if (c0 == 3u) {
+                    walking = false;
+                    break;
+                }
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (!walking) break;
+        }
+        // ---------------- boundary cells (algo.rs:195-220): row 0 holds only finite insert scores (code I), column 0 only
+        // delete scores (code D); a local alignment stops on them (algo.rs:401-405); (0,0) is never emitted after a move
+        // (algo.rs:419-421).  One long run each, cut into pieces the descriptor's run field holds.
+        if (!left_band && !local && (i == 0u) != (j == 0u)) {
+            const uint32_t c0 = (i == 0u) ? 1u : 2u;
+            uint32_t left = (i == 0u) ? j : i;
+            while (left) {
+                const uint32_t run = min(left, 1u << 16);
+                push(i, j, c0 | (prevc << 2) | (run << 4), nops);
+                prevc = c0;
+                nops += run;
+                if (c0 == 1u) j -= run;
+                else i -= run;
+                left -= run;
+            }
         }
         if (left_band && lane == 0) atomicAdd(P.left_band, 1u);
         if (lane == 0) {
-            dbg[0] = dbg_iters | (dbg_reloads << 32);
+            dbg[0] = (unsigned long long)pushed | ((unsigned long long)min(dbg_reloads, 0xffffu) << 32) |
+                     ((unsigned long long)min(dbg_miss, 0xffffu) << 48);
             dbg[1] = (unsigned long long)(clock64() - dbg_t0);
             dbg[2] = (unsigned long long)dbg_reload_cyc;
+            dbg[3] = dbg_ringwait;
         }
-        __syncwarp();
-        __threadfence_block();                            // debug counters before the end marker
-        push(0u, 0u, 0xffffffffu);                        // end of path
-    } else {
-        // ================================================================ emit warp
-        uint8_t *ops = P.ops + pd->ops_off;
-        uint32_t nops = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
-        uint32_t last = 0;  // AlignmentChoice::Match, algo.rs:338
-        uint32_t end_i = i, end_j = j;
-        if (i == 0 && j == 0) {
-            // only possible for m == n == 0: one Match at (0,0) (None == None), then both checked_sub fail
-            if (lane == 0) ops[0] = 0;
-            nops = 1;
-            n_match = 1;
-        }
-        uint32_t popped = 0;
-        for (;;) {
+        push(0u, 0u, 3u, nops);                               // end of path, one marker per emit warp
+        push(0u, 0u, 3u, nops);
+        nreq++;
+        sts_volatile_uint4(req + nreq % WALK_REQ, make_uint4(0u, 0u, 0x80000000u, nreq));   // the loader warp may leave
+    } else if (wid == 2) {
+        // ================================================================ loader warp
+        for (uint32_t seq = 1;; ++seq) {
             uint4 d;
             do {
-                d = lds_volatile_uint4(ring + popped % WALK_RING);
-            } while (d.w != popped + 1u || (d.x >> 29) != (((popped + 1u) >> 5) & 7u));
-            d.x &= 0x1fffffffu;                           // row indices stay below 2^29 (gx_check_scores)
+                d = lds_volatile_uint4(req + seq % WALK_REQ);
+            } while (d.w != seq);
+            __syncwarp();
+            if (d.z >> 31) break;
+            const uint32_t p = d.x, s_ = d.y, r0 = d.z & 0xfffu, r1 = (d.z >> 12) & 0xfffu, b = (d.z >> 24) & 3u;
+            uint32_t flag = 1u;
+            if (P.tile_codes) flag = P.tile_codes[pd->tile_base + p * pd->S + s_];
+            const uint32_t c0w = (r0 / R) / SPC;
+            const uint32_t nch = (r1 / R + 31u) / SPC - c0w + 1u;
+            GX_CHECK(P.check, b < WALK_NBUF && nch * 512u <= BUF_BYTES && (uint64_t)(c0w + nch) * 512 <= pd->tile_code_bytes &&
+                                  pd->codes_off + (uint64_t)(p * pd->S + s_ + 1) * pd->tile_code_bytes <= P.code_bytes, 23);
+            const uint4 *tile = reinterpret_cast<const uint4 *>(P.codes + pd->codes_off + (uint64_t)(p * pd->S + s_) * pd->tile_code_bytes) +
+                                (size_t)c0w * 32 + lane;
+            uint32_t dst = smem_u32(bufs + b * BUF_BYTES) + (uint32_t)lane * 16u;
+            for (uint32_t q2 = 0; q2 < nch; ++q2) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tile + (size_t)q2 * 32) : "memory");
+                dst += 32 * 16;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            __threadfence_block();                            // every lane's copies before the ready word
+            if (lane == 0) sts_volatile_u32(ready + b, seq | (flag ? 0u : 0x80000000u));
+        }
+    } else {
+        // ================================================================ emit warps: descriptors e, e + 2, e + 4, ...
+        const uint32_t e = (uint32_t)wid >> 1;
+        uint8_t *ops = P.ops + pd->ops_off;
+        uint32_t nops_end = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
+        uint32_t last_seq = 0, end_i = i, end_j = j;
+        for (uint32_t seq = e;; seq += 2u) {
+            const uint32_t tag = (seq / WALK_RING + 1u) & 7u;
+            uint4 d;
+            do {
+                d = lds_volatile_uint4(ring + seq % WALK_RING);
+            } while ((d.x >> 29) != tag || (d.z >> 29) != tag);
             __syncwarp();                                 // every lane has its copy: the slot may be reused
-            popped++;
-            if (lane == 0) sts_volatile_u32(tail, popped);
-            if (d.z == 0xffffffffu) break;
-            const uint32_t ri = d.x, rj = d.y, c0 = d.z & 3u, run = d.z >> 8;
-            const uint32_t x = (uint32_t)lane;
+            if (lane == 0) sts_volatile_u32(tail + e, seq + 1u);
+            const uint32_t c0 = d.z & 3u;
+            if (c0 == 3u) break;
+            const uint32_t ri = d.x & 0x1fffffffu, rj = d.y;              // row indices stay below 2^29 (gx_check_scores)
+            const uint32_t run = (d.z >> 4) & 0x1ffffffu, before = d.w;
             const bool diag = (c0 == 0u);
+            const bool opens = !diag && c0 != ((d.z >> 2) & 3u);      // last_choice differs (algo.rs:373-379, 388-394)
             const uint32_t di = (c0 != 1u) ? 1u : 0u, dj = (c0 != 2u) ? 1u : 0u;
-            const bool mine = x < run;
-            const uint32_t ci = ri - (mine ? x * di : 0u), cj = rj - (mine ? x * dj : 0u);
-            // labels.  Diagonal: is_match(i, j), Option<u8> equality with None == None (sequence.rs:113-114): the characters
-            // AFTER the cell's own (0-based s1[i], s2[j]; algo.rs:354).  Gaps: open/extend from last_choice (algo.rs:373-379, 388-394).
-            const bool lab = diag & mine;
-            const int a = (lab && ci < m) ? (int)__ldg(s1 + ci) : -1;
-            const int b = (lab && cj < n) ? (int)__ldg(s2 + cj) : -1;
-            const uint32_t mmask = __ballot_sync(0xffffffffu, lab && a == b);
-            const uint32_t nm = (uint32_t)__popc(mmask);
             const uint32_t ext = (c0 == 1u) ? 2u : 3u;          // Insert / Delete
-            const bool opens = !diag && (last != ext);
-            const uint32_t gop = (x == 0 && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
-            const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
-            GX_CHECK(P.check, !mine || (nops + x <= m + n && pd->ops_off + nops + x < P.ops_bytes), 22);
-            if (mine) ops[nops + x] = (uint8_t)op;
-            n_match += nm;
-            n_mis += diag ? run - nm : 0u;
+            for (uint32_t base = 0; base < run; base += 32u) {
+                const uint32_t x = base + (uint32_t)lane;
+                const bool mine = x < run;
+                const uint32_t ci = ri - (mine ? x * di : 0u), cj = rj - (mine ? x * dj : 0u);
+                // labels.  Diagonal: is_match(i, j), Option<u8> equality with None == None (sequence.rs:113-114): the characters
+                // AFTER the cell's own (0-based s1[i], s2[j]; algo.rs:354).  Gaps: open/extend from last_choice (algo.rs:373-379, 388-394).
+                const bool lab = diag & mine;
+                const int a = (lab && ci < m) ? (int)__ldg(s1 + ci) : -1;
+                const int b = (lab && cj < n) ? (int)__ldg(s2 + cj) : -1;
+                const uint32_t nm = (uint32_t)__popc(__ballot_sync(0xffffffffu, lab && a == b));
+                const uint32_t gop = (x == 0u && opens) ? ext + 2u : ext;   // OpenInsert = 4, OpenDelete = 5
+                const uint32_t op = diag ? ((a == b) ? 0u : 1u) : gop;
+                GX_CHECK(P.check, !mine || ((uint64_t)before + x <= (uint64_t)m + n && pd->ops_off + before + x < P.ops_bytes), 22);
+                if (mine) ops[before + x] = (uint8_t)op;
+                n_match += nm;
+                n_mis += diag ? min(32u, run - base) - nm : 0u;
+            }
             n_open += opens ? 1u : 0u;
             n_ext += diag ? 0u : (opens ? run - 1u : run);
-            last = diag ? 0u : ext;
-            nops += run;
+            last_seq = seq + 1u;
+            nops_end = before + run;
             end_i = ri - (run - 1u) * di;                 // last emitted cell
             end_j = rj - (run - 1u) * dj;
         }
-        res.end_i = end_i;
-        res.end_j = end_j;
-        res.n_ops = nops;
-        res.matches = n_match;
-        res.mismatches = n_mis;
-        res.gap_extensions = n_ext;
-        res.opening_gaps = n_open;
+        if (lane == 0) {
+            uint32_t *pp = part + e * 8u;
+            pp[0] = n_match;
+            pp[1] = n_mis;
+            pp[2] = n_ext;
+            pp[3] = n_open;
+            pp[4] = last_seq;
+            pp[5] = end_i;
+            pp[6] = end_j;
+            pp[7] = nops_end;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t *p0 = part, *p1 = part + 8;
+        const uint32_t *pl = (p1[4] > p0[4]) ? p1 : p0;       // the emit warp that handled the last run
+        if (pl[4] != 0u) {
+            res.end_i = pl[5];
+            res.end_j = pl[6];
+            res.n_ops = pl[7];
+        }
+        res.matches = p0[0] + p1[0];
+        res.mismatches = p0[1] + p1[1];
+        res.gap_extensions = p0[2] + p1[2];
+        res.opening_gaps = p0[3] + p1[3];
         if (P.debug) {
             res.lcs_at_first_max = dbg[0];
             res.fill_ms = (double)dbg[1];
             res.walk_ms = (double)dbg[2];
+            res.start_i |= dbg[3] << 32;                       // ring-full waits of the path warp
         }
-        if (lane == 0) P.results[q] = res;
+        P.results[q] = res;
     }
 }
 
