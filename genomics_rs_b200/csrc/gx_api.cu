@@ -154,7 +154,7 @@ static Tunables read_tunables() {
     t.start_lead = env_int("GX_START_LEAD", 0);
     t.fill_stats = env_int("GX_FILL_STATS", 0);
     t.walk_stats = getenv("GX_WALK_STATS") ? 1 : 0;
-    t.walk_rows = env_int("GX_WALK_ROWS", 0);          // 256 / 512: rows of a code window of the walk
+    t.walk_rows = env_int("GX_WALK_ROWS", 0);          // 64..512, multiple of 64: rows of a code window of the walk
     t.no_stream = getenv("GX_NO_STREAM") ? 1 : 0;
     t.reads32 = getenv("GX_READS32") ? 1 : 0;
     t.test_abort = getenv("GX_TEST_ABORT") ? 1 : 0;
@@ -340,9 +340,21 @@ static int launch_walk(gx_plan *pl, WalkParams wp) {
         return GX_ERR_INTERNAL;
     }
     // rows of a code window: 512 lets a diagonal path cross a whole strip (32*K <= 256 columns for K <= 8) inside one window;
-    // 256 keeps more walk CTAs resident per SM when there are many pairs (three window buffers per CTA)
-    uint32_t rows = (pl->K <= 8 && pl->n_pairs <= 2u * (uint32_t)pl->ctx->sm_count) ? 512u : 256u;
-    if (pl->tun.walk_rows == 256 || pl->tun.walk_rows == 512) rows = (uint32_t)pl->tun.walk_rows;
+    // fewer rows (three window buffers per CTA) keep every pair's walk CTA resident when there are many pairs -- the walk is a
+    // latency chain per pair, so residency is its throughput; short sequences need no more rows than they have
+    const uint32_t row_cap = (uint32_t)std::max<uint64_t>(64, std::min<uint64_t>(512, (pl->max_len + 63) / 64 * 64));
+    uint32_t rows = 0;
+    for (uint32_t cand : {512u, 384u, 256u, 192u, 128u, 64u}) {
+        if (cand > 256u && pl->K > 8) continue;
+        const uint32_t r_ = std::min(cand, row_cap);
+        const uint32_t per_sm = std::min<uint32_t>(2048u / WALK_THREADS, (227u * 1024u) / (walk_smem_bytes(pl->K, pl->R, r_) + 1024u));
+        if (pl->n_pairs <= (uint64_t)per_sm * (uint64_t)pl->ctx->sm_count) {
+            rows = r_;
+            break;
+        }
+    }
+    if (!rows) rows = pl->max_len <= 256 ? 64u : 128u;     // more pairs than fit at once: many CTAs per SM
+    if (pl->tun.walk_rows >= 64 && pl->tun.walk_rows <= 512 && pl->tun.walk_rows % 64 == 0) rows = (uint32_t)pl->tun.walk_rows;
     wp.win_rows = rows;
     const uint32_t smem = wp.traceback ? walk_smem_bytes(pl->K, pl->R, rows) : 0u;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_bytes(pl->K, pl->R, 512u)));
