@@ -38,7 +38,8 @@ constexpr uint32_t WALK_CTRL_BYTES = 2048;
 constexpr uint32_t WALK_RING = 64;          // run descriptors in flight between the path warp and the emit warps
 constexpr uint32_t WALK_REQ = 8;            // window requests in flight between the path warp and the loader warp (<= 3 used)
 constexpr uint32_t WALK_NBUF = 3;           // window buffers: the current one and two prefetch targets
-constexpr uint32_t WALK_THREADS = 128;
+constexpr uint32_t WALK_EMIT = 2;            // emit warps (<= 4: their tails are read with one 16-byte load)
+constexpr uint32_t WALK_THREADS = 64 + 32 * WALK_EMIT;   // path warp, emit warp 0, loader warp, emit warps 1..
 __host__ __device__ constexpr uint32_t walk_smem_bytes(int K, int R, uint32_t rows) {
     return WALK_CTRL_BYTES + WALK_NBUF * walk_buf_bytes(K, R, rows);
 }
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
     const uint32_t BUF_BYTES = walk_buf_bytes(K, R, WR);
     extern __shared__ __align__(16) uint8_t walk_smem[];
     // descriptor ring, LL style: {i | tag, j, direction | previous direction << 2 | run << 4 | tag, ops emitted before}.  The path warp
-    // writes a descriptor with ONE 16-byte shared-memory store and the emit warp it belongs to (sequence number parity) polls
+    // writes a descriptor with ONE 16-byte shared-memory store and the emit warp it belongs to (sequence number mod WALK_EMIT) polls
     // the slot until it carries the lap tag it expects: no head word, no fence on the path warp's dependent chain.
     // tail[e] (descriptors emit warp e is done with) is only read when the ring looks full.
     uint4 *ring = reinterpret_cast<uint4 *>(walk_smem);
@@ -171,11 +172,12 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
     uint32_t *tail = reinterpret_cast<uint32_t *>(walk_smem + WALK_RING * 16 + WALK_REQ * 16);
     uint32_t *ready = tail + 4;                                                        // per buffer: last request finished | no-codes << 31
     uint32_t *part = tail + 8;                                                         // per emit warp: 8 words of partial results
-    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(tail + 24);
+    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(tail + 8 + 8 * WALK_EMIT);
+    uint32_t *scratch = tail + 16 + 8 * WALK_EMIT;                                     // 64 words
     uint8_t *bufs = walk_smem + WALK_CTRL_BYTES;
     if (threadIdx.x < WALK_RING) ring[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);       // lap tags start at 1
     if (threadIdx.x < WALK_REQ) req[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);         // request numbers start at 1
-    if (threadIdx.x < 32) tail[threadIdx.x] = 0u;                                       // tails, ready words, partial results
+    if (threadIdx.x < 16 + 8 * WALK_EMIT) tail[threadIdx.x] = 0u;                       // tails, ready words, partial results, debug counters
     __syncthreads();
 
     if (wid == 0) {
@@ -185,7 +187,6 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
         // from %tid / the CTA's shared window inside the loop (it otherwise does, with 20-clock S2R / S2UR reads per run).
         uint32_t y, ring_s;
         {
-            uint32_t *scratch = tail + 32;
             sts_volatile_u32(scratch + lane, 31u - (uint32_t)lane);
             sts_volatile_u32(scratch + 32 + lane, smem_u32(ring));
             y = lds_volatile_u32(scratch + lane);
@@ -197,8 +198,13 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
         auto push = [&](uint32_t pi, uint32_t pj, uint32_t meta, uint32_t before) __attribute__((always_inline)) {
             if (pushed >= safe) {           // slot reuse: its previous descriptor (RING back) must have been consumed
                 dbg_ringwait++;
-                do {                        // tail[e] = 1 + the last descriptor emit warp e is done with: everything below both is consumed
-                    safe = min(lds_volatile_u32(tail), lds_volatile_u32(tail + 1)) + WALK_RING;
+                do {                        // tail[e] = 1 + the last descriptor emit warp e is done with: everything below all of them is consumed
+                    const uint4 tl = lds_volatile_uint4(reinterpret_cast<const uint4 *>(tail));
+                    uint32_t lo = tl.x;
+                    if (WALK_EMIT > 1) lo = min(lo, tl.y);
+                    if (WALK_EMIT > 2) lo = min(lo, tl.z);
+                    if (WALK_EMIT > 3) lo = min(lo, tl.w);
+                    safe = lo + WALK_RING;
                 } while (pushed >= safe);
             }
             // the lap tag rides in both 8-byte halves: a reader that caught the halves from different laps -- should
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
 
         // ---- window state
         uint32_t cbase = 0;                 // shared-memory address of the current window buffer
-        int rrel = 0, jw = 0, woff = 0;     // row relative to the buffer's first chunk, column in the strip, first window row (same base)
+        int rrel = 0, jw = 0;               // row inside the window (= inside the buffer), column in the strip
         uint32_t cb = 0;                    // current buffer
         // what each buffer holds / will hold: tile (bp, bs), panel rows [br0, br1], the request that fills it
         uint32_t bp[WALK_NBUF], bs[WALK_NBUF], br0[WALK_NBUF], br1[WALK_NBUF], bq[WALK_NBUF];
@@ -229,13 +235,33 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
         };
         // code of the window cell (row rr relative to the buffer's first chunk, column jc of the strip): 0 S / 1 I / 2 D / 3 stop
         auto code_at = [&](uint32_t rr, uint32_t jc) __attribute__((always_inline)) -> uint32_t {
-            const uint32_t l = jc / K, t = rr / R + l;            // the step at which fill-lane l worked on this row's block
-            const uint32_t idx2 = ((t / SPC) * 32u + l) * 64u + ((t % SPC) * R + rr % R) * K + jc % K;
-            GX_CHECK(P.check, (idx2 >> 4) * 4u < BUF_BYTES, 21);
-            const uint32_t word = lds_code_word(cbase + (idx2 >> 4) * 4u);
-            return (word >> ((idx2 & 15u) * 2u)) & 3u;
+            uint32_t off, sh;
+            if constexpr (R == 1 && K >= 4) {
+                // 64 cells (SPC steps x K columns) per 16-byte unit [chunk][fill-lane]; with u = t * K the cell is entry
+                // (u & 63) | k of unit (u >> 6, l).  Written out so that the chain from (rr, jc) to the address is five
+                // instructions deep (t, v, two masks, multiply-add, add)
+                constexpr uint32_t LK = (K == 4) ? 2u : (K == 8) ? 3u : 4u;
+                static_assert(K == 4 || K == 8 || K == 16, "code_at: K");
+                const uint32_t l = jc >> LK, t = rr + l;          // the step at which fill-lane l worked on this row
+                const uint32_t v = t << (LK - 2u);                // u >> 2
+                off = (v & ~15u) * 32u + (v & 12u) + (l << 4);    // (u >> 6) * 512 + l * 16 + (entry >> 4) * 4
+                sh = ((((t << LK) | (jc & (K - 1u))) & 15u)) * 2u;
+            } else {
+                const uint32_t l = jc / K, t = rr / R + l;        // the step at which fill-lane l worked on this row's block
+                const uint32_t idx2 = ((t / SPC) * 32u + l) * 64u + ((t % SPC) * R + rr % R) * K + jc % K;
+                off = (idx2 >> 4) * 4u;
+                sh = (idx2 & 15u) * 2u;
+            }
+            GX_CHECK(P.check, off < BUF_BYTES, 21);
+            const uint32_t word = lds_code_word(cbase + off);
+            return (word >> sh) & 3u;
         };
 
+        // first row of the window that ends at panel row r1: WR rows, rounded down to a code chunk's first row, so that the
+        // row inside the buffer is the row inside the window (no offset on the chain)
+        auto win_r0 = [&](uint32_t r1) __attribute__((always_inline)) -> uint32_t {
+            return ((r1 >= WR - 1u) ? r1 - (WR - 1u) : 0u) / (SPC * R) * (SPC * R);
+        };
         uint32_t dbg_reloads = 0, dbg_miss = 0;
         long long dbg_reload_cyc = 0;
         bool left_band = false;
@@ -255,7 +281,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                 // neither prediction holds this cell: load the window that ends at this row into the buffer just left
                 dbg_miss++;
                 hit = cb;
-                const uint32_t r0 = (tr >= WR - 1u) ? tr - (WR - 1u) : 0u;
+                const uint32_t r0 = win_r0(tr);
                 const uint32_t sq = post(hit, tp, ts, r0, tr);
 #pragma unroll
                 for (uint32_t b = 0; b < WALK_NBUF; ++b)
@@ -268,12 +294,11 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                     }
             }
             cb = hit;
-            uint32_t wr0 = 0, wr1 = 0, wq = 0;
+            uint32_t wr0 = 0, wq = 0;
 #pragma unroll
             for (uint32_t b = 0; b < WALK_NBUF; ++b)
                 if (b == cb) {
                     wr0 = br0[b];
-                    wr1 = br1[b];
                     wq = bq[b];
                 }
             uint32_t st;
@@ -287,12 +312,9 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                 left_band = true;
                 break;
             }
-            const uint32_t wc0 = (wr0 / R) / SPC;
             cbase = smem_u32(bufs + cb * BUF_BYTES);
-            rrel = (int)(tr - wc0 * SPC * R);
-            woff = (int)(wr0 - wc0 * SPC * R);
+            rrel = (int)(tr - wr0);                               // wr0 is the first row of the buffer's first chunk
             jw = (int)(jj % G::W);
-            asm volatile("" : "+r"(rrel), "+r"(woff), "+r"(jw), "+r"(cbase));   // loop-carried registers, not expressions to re-derive per run
             uint32_t c0 = code_at((uint32_t)rrel, (uint32_t)jw);
             // ask for the windows the walk will probably need next, into the two other buffers.  A diagonal path leaves this
             // window on the left after jw + 1 rows: the left neighbour strip around that row, with WR/4 rows of slack below it
@@ -301,14 +323,15 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                 uint32_t o1 = (cb + 1u) % WALK_NBUF, o2 = (cb + 2u) % WALK_NBUF;
                 const int pred = (int)tr - (int)(jw + 1);
                 const bool want_left = ts > 0 && pred + (int)(WR / 4u) >= 0;
-                const bool want_top = wr0 > 0 || tp > 0;
+                // (the rows above only when the path can get there before it leaves on the left: not for a full-height window)
+                const bool want_top = (wr0 > 0 || tp > 0) && (!want_left || pred < (int)(wr0 + WR / 4u));
                 uint32_t lp = 0xffffffffu, ls = 0, lr0 = 0, lr1 = 0, lq = 0;
                 uint32_t up = 0xffffffffu, us = 0, ur0 = 0, ur1 = 0, uq = 0;
                 if (want_left) {
                     lp = tp;
                     ls = ts - 1u;
                     lr1 = (uint32_t)min((int)tr, pred + (int)(WR / 4u));
-                    lr0 = (lr1 >= WR - 1u) ? lr1 - (WR - 1u) : 0u;
+                    lr0 = win_r0(lr1);
                     lq = post(o1, lp, ls, lr0, lr1);
                 }
                 if (want_top) {
@@ -316,7 +339,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                     if (wr0 > 0) {
                         up = tp;
                         ur1 = wr0 - 1u;
-                        ur0 = (ur1 >= WR - 1u) ? ur1 - (WR - 1u) : 0u;
+                        ur0 = win_r0(ur1);
                     } else {
                         up = tp - 1u;
                         ur1 = PANEL_H - 1;
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                 // lane y looks y moves ahead in the direction of c0, as far as the window reaches; the run ends at the
                 // first different code.  Window cells are interior cells (i, j >= 1): no boundary cases on this chain.
                 const bool mi = (c0 != 1u), mj = (c0 != 2u);
-                const uint32_t a = mi ? (uint32_t)(rrel - woff) : 31u, bcol = mj ? (uint32_t)jw : 31u;
+                const uint32_t a = mi ? (uint32_t)rrel : 31u, bcol = mj ? (uint32_t)jw : 31u;
                 const uint32_t lim = min(a, bcol);
                 const uint32_t ys = __vimin3_u32(y, a, bcol);
                 const uint32_t cx = code_at((uint32_t)rrel - (mi ? ys : 0u), (uint32_t)jw - (mj ? ys : 0u));
@@ -376,7 +399,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
                         walking = false;
                         break;
                     }
-                    if (rrel < woff || jw < 0) break;
+                    if (rrel < 0 || jw < 0) break;
                     c0 = code_at((uint32_t)rrel, (uint32_t)jw);
                 }
                 if (c0 == 3u) {
@@ -410,8 +433,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
             dbg[2] = (unsigned long long)dbg_reload_cyc;
             dbg[3] = dbg_ringwait;
         }
-        push(0u, 0u, 3u, nops);                               // end of path, one marker per emit warp
-        push(0u, 0u, 3u, nops);
+        for (uint32_t e = 0; e < WALK_EMIT; ++e) push(0u, 0u, 3u, nops);   // end of path, one marker per emit warp
         nreq++;
         sts_volatile_uint4(req + nreq % WALK_REQ, make_uint4(0u, 0u, 0x80000000u, nreq));   // the loader warp may leave
     } else if (wid == 2) {
@@ -445,11 +467,11 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
         }
     } else {
         // ================================================================ emit warps: descriptors e, e + 2, e + 4, ...
-        const uint32_t e = (uint32_t)wid >> 1;
+        const uint32_t e = (wid == 1) ? 0u : (uint32_t)wid - 2u;
         uint8_t *ops = P.ops + pd->ops_off;
         uint32_t nops_end = 0, n_match = 0, n_mis = 0, n_ext = 0, n_open = 0;
         uint32_t last_seq = 0, end_i = i, end_j = j;
-        for (uint32_t seq = e;; seq += 2u) {
+        for (uint32_t seq = e;; seq += WALK_EMIT) {
             const uint32_t tag = (seq / WALK_RING + 1u) & 7u;
             uint4 d;
             do {
@@ -503,17 +525,25 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t *p0 = part, *p1 = part + 8;
-        const uint32_t *pl = (p1[4] > p0[4]) ? p1 : p0;       // the emit warp that handled the last run
+        const uint32_t *pl = part;                            // the emit warp that handled the last run
+        uint32_t nm = 0, nx = 0, ne = 0, no = 0;
+        for (uint32_t e = 0; e < WALK_EMIT; ++e) {
+            const uint32_t *pe = part + e * 8u;
+            if (pe[4] > pl[4]) pl = pe;
+            nm += pe[0];
+            nx += pe[1];
+            ne += pe[2];
+            no += pe[3];
+        }
         if (pl[4] != 0u) {
             res.end_i = pl[5];
             res.end_j = pl[6];
             res.n_ops = pl[7];
         }
-        res.matches = p0[0] + p1[0];
-        res.mismatches = p0[1] + p1[1];
-        res.gap_extensions = p0[2] + p1[2];
-        res.opening_gaps = p0[3] + p1[3];
+        res.matches = nm;
+        res.mismatches = nx;
+        res.gap_extensions = ne;
+        res.opening_gaps = no;
         if (P.debug) {
             res.lcs_at_first_max = dbg[0];
             res.fill_ms = (double)dbg[1];

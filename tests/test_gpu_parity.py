@@ -303,6 +303,29 @@ def test_code_band_kernel_ragged(gx, oracle, k, r, chain1, monkeypatch):
         plan.close()
 
 
+_WINDOW_ORACLE = {}
+
+
+@pytest.mark.parametrize("rows", [64, 128, 256, 512])
+@pytest.mark.parametrize("k,r", KR_COMBOS)
+def test_walk_window_sizes(gx, oracle, k, r, rows, monkeypatch):
+    """the walk's code windows (GX_WALK_ROWS forces their height) for every strip width: paths that cross strip and panel
+    (4096 rows) boundaries, leave a window on the left and at the top, run along long gaps (one sequence a fragment of the
+    other: hundreds of consecutive Insert / Delete ops) and end on row 0 / column 0"""
+    force_kr(monkeypatch, k, r)
+    monkeypatch.setenv("GX_WALK_ROWS", str(rows))
+    rng = np.random.default_rng(23)
+    pairs = [random_pair(rng, m, n, similar=True, sub=0.08, indel=0.02) for m, n in [(4300, 4250), (8200, 8300), (1500, 600), (700, 5000)]]
+    a, b = random_pair(rng, 6000, 6000, similar=True, sub=0.05, indel=0.005)
+    pairs += [(a, b[1500:4700]), (a[300:5100], b), (a[:4100], a[:4100]), (a[5000:], b[:900])]
+    for is_local in (False, True):
+        got = gx.align_batch(pairs, CONFIG_TOML, is_local)
+        for x, ((s1, s2), res) in enumerate(zip(pairs, got)):
+            if (x, is_local) not in _WINDOW_ORACLE:
+                _WINDOW_ORACLE[(x, is_local)] = oracle.align_linear(s1, s2, CONFIG_TOML, is_local)
+            _same(res, _WINDOW_ORACLE[(x, is_local)], oracle, f"pair {x} m={len(s1)} n={len(s2)} local={is_local} K={k} rows={rows}")
+
+
 def test_corona_all_vs_all(gx, oracle, goldens):
     """BASELINE config 3: 45 pairs of ~30 kb genomes, global, score + traceback, one batch."""
     order = goldens["corona_order"]
