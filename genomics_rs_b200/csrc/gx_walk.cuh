@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(WALK_THREADS) gx_walk_kernel(const WalkParams 
 
     using G = Geo<K, R>;
     constexpr uint32_t SPC = G::SPC;
-    const uint32_t WR = P.win_rows;                          // rows per window (256 or 512); a window spans the strip's width
+    const uint32_t WR = P.win_rows;                          // rows per window (64..512, chosen per launch); a window spans the strip's width
     const uint32_t BUF_BYTES = walk_buf_bytes(K, R, WR);
     extern __shared__ __align__(16) uint8_t walk_smem[];
     // descriptor ring, LL style: {i | tag, j, direction | previous direction << 2 | run << 4 | tag, ops emitted before}.  The path warp
