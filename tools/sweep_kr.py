@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--chain", default="0,1")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--batch", default="", help="comma list of GX_BATCH values (steps per hand-off batch) to force, e.g. 8,16,32")
+    ap.add_argument("--auto-only", action="store_true", help="only the configuration the library picks itself")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_kr.jsonl"))
     args = ap.parse_args()
     combos = [tuple(int(x) for x in c.split("x")) for c in args.combos.split(",") if c] or ALL
@@ -63,7 +64,7 @@ def main():
         cells = int(((len1 + 1) * (len2 + 1)).sum())
         ref = None
         batches = [int(b) for b in args.batch.split(",") if b] or [0]
-        for k, r, bsteps in [(0, 0, 0)] + [(k, r, b) for k, r in combos for b in batches]:
+        for k, r, bsteps in [(0, 0, 0)] + ([] if args.auto_only else [(k, r, b) for k, r in combos for b in batches]):
             for c in ([-1] if k == 0 else chains):
                 for var in ("GX_K", "GX_R", "GX_CHAIN1", "GX_BATCH"):
                     os.environ.pop(var, None)
