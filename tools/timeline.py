@@ -26,3 +26,8 @@ for k in order[: int(sys.argv[3]) if len(sys.argv) > 3 else 40]:
     print(f"p={int(p[k])} s={int(s[k]):4d} sm={int(sm[k]):3d} take {(tl[k,0]-t0)/1e3:9.1f} us  dp0 {(tl[k,1]-t0)/1e3:9.1f}  end {(tl[k,2]-t0)/1e3:9.1f}  run {(tl[k,2]-tl[k,1])/1e3:8.1f} us")
 d = np.diff(np.array([tl[k, 1] for k in order if p[k] == 0], dtype=np.float64))
 print("panel 0: start-to-start lag between adjacent strips: median %.2f us, mean %.2f us, max %.2f" % (np.median(d) / 1e3, d.mean() / 1e3, d.max() / 1e3))
+rows0 = min(m, 4096)
+run0 = np.array([float(tl[k, 2] - tl[k, 1]) for k in order if p[k] == 0])
+step_ns = np.median(run0) / (rows0 + 31)
+print("panel 0: tile run time median %.1f us = %.1f ns per step (%d rows + 31 steps of skew): lag = %.1f steps per strip; %d strips"
+      % (np.median(run0) / 1e3, step_ns, rows0, np.median(d) / step_ns, len(run0)))
